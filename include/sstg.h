@@ -1,0 +1,136 @@
+/*
+ * sstg.h -- C ABI of the B200-native Social-STGCNN hot path (libsstg.so).
+ *
+ * The reference (GRatTWCU/Social-STGCNN) is pure Python and has no FFI boundary; its
+ * boundary is the Python API.  Each entry point below therefore cites the reference
+ * FUNCTION it replaces (file:line under the reference tree), and
+ * social_stgcnn_b200/{utils,model,metrics}.py put the reference's own signatures back on
+ * top of these calls (INTEGRATION.md shows the binding).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless its name ends in _host;
+ *   - all tensors are fp32, densely packed, 16-byte aligned at the base;
+ *   - a batch is a list of S scenes with ragged pedestrian counts N_s, segment-packed:
+ *       seg_off[S+1]  int32  prefix sum of N_s              (pedestrian index space, P = seg_off[S])
+ *       a_off[S+1]    int64  float offset of scene s's (T,N_s,N_s) adjacency block; every
+ *                            entry is a multiple of 4 floats (16 B) -- see sstg_plan_host
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
+ *   - nothing here allocates or synchronises: the caller owns every buffer, the calls
+ *     are stream-ordered and thread-safe (no global state);
+ *   - return value: 0 on success, a negative SSTG_E* code otherwise (sstg_error_string).
+ *
+ * Model dimensions are those of every shipped checkpoint (train.py:127-136):
+ * input_feat 2, output_feat 5, obs_seq_len 8, pred_seq_len 12, n_stgcnn 1, n_txpcnn 5, kernel 3.
+ */
+#ifndef SSTG_H_
+#define SSTG_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SSTG_T_OBS 8
+#define SSTG_T_PRED 12
+#define SSTG_C_IN 2
+#define SSTG_C 5
+#define SSTG_N_PARAMS 7563 /* named_parameters() order of model.py:157-178 */
+#define SSTG_N_BN 30       /* running_mean[5], running_var[5] of tcn.0, tcn.3, residual.1 */
+#define SSTG_MAX_PEDS 256  /* largest scene the kernels accept (shared-memory bound) */
+#define SSTG_XTILE_COLS 128 /* TXP-CNN tile: whole scenes up to this many pedestrian columns */
+#define SSTG_XTILE_MAX_SCENES 32
+
+/* flags of sstg_graph_build */
+#define SSTG_GRAPH_NORM_LAP 1 /* norm_lap_matr=True (utils.py:48-50) */
+#define SSTG_GRAPH_FP64 2     /* fp64 islands exactly as the reference (bit-exact vs networkx); default fp32 */
+#define SSTG_GRAPH_V_ONLY 4   /* only the node tensor V (the A_tr the reference builds is never consumed) */
+
+/* flags of sstg_sample_ade_fde */
+#define SSTG_EVAL_FP64_DIST 1 /* per-step distance sqrt in fp64 exactly as math.sqrt in metrics.py:33,50 */
+
+#define SSTG_OK 0
+#define SSTG_EINVAL (-1)    /* bad argument (null pointer, negative size, misaligned) */
+#define SSTG_ETOOBIG (-2)   /* a scene exceeds SSTG_MAX_PEDS */
+#define SSTG_ECUDA (-3)     /* a CUDA runtime call failed; see sstg_last_cuda_error */
+#define SSTG_EARCH (-4)     /* device is not sm_100 */
+
+int sstg_version(void);
+const char* sstg_error_string(int code);
+/* text of the last CUDA error seen by THIS thread inside the library ("" if none) */
+const char* sstg_last_cuda_error(void);
+
+/* ---- host-side planning (pure CPU, no CUDA) ---------------------------------------
+ * From the per-scene pedestrian counts compute the packed-batch offsets and the
+ * TXP-CNN tile table.  seg_off_host[S+1], a_off_host[S+1], tile_off_host[S+1] are
+ * caller-provided; tile t covers scenes [tile_off[t], tile_off[t+1]).
+ * Outputs *n_tiles, *max_n, *a_floats (total floats of the packed A buffer, padded).
+ * Replaces the `seq_start_end` bookkeeping of TrajectoryDataset (utils.py:186-190). */
+int sstg_plan_host(const int32_t* n_peds_host, int32_t S, int32_t T,
+                   int32_t* seg_off_host, int64_t* a_off_host, int32_t* tile_off_host,
+                   int32_t* n_tiles, int32_t* max_n, int64_t* a_floats);
+
+/* ---- (1) graph construction --------------------------------------------------------
+ * Replaces utils.seq_to_graph + anorm (utils.py:23-53) incl. the networkx
+ * normalized_laplacian_matrix call (utils.py:49-50), for every scene of a packed batch.
+ *   rel   [P,2,T]   per-pedestrian relative displacements, the layout of
+ *                   TrajectoryDataset.obs_traj_rel / pred_traj_rel (utils.py:180-183)
+ *   V     scene s at float offset seg_off[s]*T*2, layout (T,N_s,2)   (utils.py:42)
+ *   A     scene s at float offset a_off[s],       layout (T,N_s,N_s) (utils.py:43-50)
+ * A may be NULL iff SSTG_GRAPH_V_ONLY. */
+int sstg_graph_build(const float* rel, const int32_t* seg_off, const int64_t* a_off,
+                     int32_t S, int32_t T, int32_t max_n,
+                     float* V, float* A, int32_t flags, void* stream);
+
+/* ---- (2) st_gcn block, eval mode ----------------------------------------------------
+ * Replaces st_gcn.forward (model.py:145-155) = ConvTemporalGraphical (model.py:64-68:
+ * 1x1 conv + einsum('nctv,tvw->nctw')) + BN + PReLU + (3,1) conv + BN + residual + PReLU,
+ * BatchNorm in eval form from the running statistics `bn`.
+ *   V  as written by sstg_graph_build with T = 8;  A likewise
+ *   H  scene s at float offset seg_off[s]*40, layout (5,8,N_s)   [model.py:185 output]
+ * `sm_count` <= 0 means "use the device's SM count" (persistent grid). */
+int sstg_stgcn_forward(const float* V, const float* A, const int32_t* seg_off, const int64_t* a_off,
+                       int32_t S, int32_t max_n, const float* params, const float* bn,
+                       float* H, int32_t sm_count, void* stream);
+
+/* ---- (3) TXP-CNN --------------------------------------------------------------------
+ * Replaces model.py:187-195: flat view (5,8,N)->(8,5,N), tpcnns[0..3] (3x3, time as
+ * channels) with PReLU and residuals, tpcnn_ouput, flat view (12,5,N)->(5,12,N).
+ *   H    as written by sstg_stgcn_forward
+ *   out  scene s at float offset seg_off[s]*60, layout (5,12,N_s) == V_pred[0] of
+ *        social_stgcnn.forward (model.py:198)
+ *   tile_off [n_tiles+1] from sstg_plan_host (device copy). */
+int sstg_txpcnn_forward(const float* H, const int32_t* seg_off, const int32_t* tile_off,
+                        int32_t n_tiles, int32_t max_n, const float* params,
+                        float* out, void* stream);
+
+/* ---- (4a) bivariate Gaussian NLL, forward -------------------------------------------
+ * Replaces metrics.bivariate_loss (metrics.py:84-113) per scene.
+ *   Vpred  (5,12,N_s) blocks as written by sstg_txpcnn_forward
+ *   Vtr    (12,N_s,2) blocks (sstg_graph_build on pred_traj_rel with T = 12)
+ *   loss   [S] per-scene mean over the 12*N_s elements */
+int sstg_nll_forward(const float* Vpred, const float* Vtr, const int32_t* seg_off, int32_t S,
+                     float* loss, void* stream);
+
+/* ---- (4b) K-sample trajectory sampling + ADE/FDE, min over samples ------------------
+ * Replaces the per-scene body of test() (test.py:59-123) with metrics.ade / fde /
+ * nodes_rel_to_nodes_abs (metrics.py:21-75): Cholesky factor of the 2x2 covariance,
+ * sample_k = mean + L eps_k, rel->abs prefix sums from the last observed position,
+ * per-pedestrian ADE/FDE, independent minima over the K samples.
+ *   last_obs [P,2]     obs_traj[:, :, -1]                      (test.py:84-85); P = total_peds = seg_off[S]
+ *   eps      scene s at float offset seg_off[s]*K*24, layout (K,12,N_s,2); standard-normal
+ *            noise to inject.  NULL = draw in-kernel with Philox4x32-10 keyed by `seed`
+ *            (counter = (k*6 + t/2, 0, global pedestrian index)).
+ *   eps_out  optional, same layout: the noise actually used (for replay); may be NULL
+ *   min_ade, min_fde [P] float64                                (test.py:121-123)
+ *   pred_abs optional (K,12,N_s,2) blocks at seg_off[s]*K*24: raw_data_dict['pred'] (test.py:105) */
+int sstg_sample_ade_fde(const float* Vpred, const float* Vtr, const float* last_obs,
+                        const int32_t* seg_off, int32_t S, int32_t total_peds, int32_t K,
+                        const float* eps, uint64_t seed, float* eps_out,
+                        double* min_ade, double* min_fde, float* pred_abs,
+                        int32_t flags, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SSTG_H_ */

@@ -1,0 +1,77 @@
+"""ctypes binding of libsstg.so (C ABI declared in include/sstg.h).
+
+There is deliberately no fallback: if the CUDA library is missing or a call
+fails, a RuntimeError is raised.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "libsstg.so")
+
+T_OBS, T_PRED, C_IN, C_OUT = 8, 12, 2, 5
+N_PARAMS, N_BN, MAX_PEDS = 7563, 30, 256
+XTILE_COLS, XTILE_MAX_SCENES = 128, 32
+GRAPH_NORM_LAP, GRAPH_FP64, GRAPH_V_ONLY = 1, 2, 4
+EVAL_FP64_DIST = 1
+
+_p = C.c_void_p
+_i32, _i64, _u64 = C.c_int32, C.c_int64, C.c_uint64
+_SIGS = {
+    "sstg_version": (C.c_int, []),
+    "sstg_error_string": (C.c_char_p, [C.c_int]),
+    "sstg_last_cuda_error": (C.c_char_p, []),
+    "sstg_plan_host": (C.c_int, [_p, _i32, _i32, _p, _p, _p, _p, _p, _p]),
+    "sstg_graph_build": (C.c_int, [_p, _p, _p, _i32, _i32, _i32, _p, _p, _i32, _p]),
+    "sstg_stgcn_forward": (C.c_int, [_p, _p, _p, _p, _i32, _i32, _p, _p, _p, _i32, _p]),
+    "sstg_txpcnn_forward": (C.c_int, [_p, _p, _p, _i32, _i32, _p, _p, _p]),
+    "sstg_nll_forward": (C.c_int, [_p, _p, _p, _i32, _p, _p]),
+    "sstg_sample_ade_fde": (C.c_int, [_p, _p, _p, _p, _i32, _i32, _i32, _p, _u64, _p, _p, _p, _p, _i32, _p]),
+}
+# entry points added by later kernels; bound only if the library exports them
+_OPTIONAL_SIGS = {
+    "sstg_forward_train": (C.c_int, [_p, _p, _p, _p, _p, _i32, _i32, _i32, _p, _p, _p, _p, _p, _p, _p]),
+    "sstg_backward": (C.c_int, [_p, _p, _p, _p, _p, _i32, _i32, _i32, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
+}
+
+_lock = threading.Lock()
+_lib = None
+
+
+def load():
+    """Load libsstg.so once; raises RuntimeError (never falls back) if absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: the CUDA library has not been built. "
+                "Run `python -m social_stgcnn_b200.build` (needs nvcc). There is no CPU fallback.")
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGS.items():
+            fn = getattr(lib, name)
+            fn.restype, fn.argtypes = res, args
+        for name, (res, args) in _OPTIONAL_SIGS.items():
+            if hasattr(lib, name):
+                fn = getattr(lib, name)
+                fn.restype, fn.argtypes = res, args
+        _lib = lib
+    return _lib
+
+
+def check(code: int, what: str) -> None:
+    if code != 0:
+        lib = load()
+        msg = lib.sstg_error_string(code).decode()
+        cuda = lib.sstg_last_cuda_error().decode()
+        raise RuntimeError(f"{what} failed: {msg} (code {code})" + (f" [{cuda}]" if cuda and code == -3 else ""))
+
+
+def exported_symbols():
+    return list(_SIGS)

@@ -1,0 +1,212 @@
+// Kernel (1): per-scene graph construction for a segment-packed batch of scenes.
+//
+// Replaces reference utils.py:23-53 (anorm + seq_to_graph + networkx
+// normalized_laplacian_matrix).  For every scene s and timestep t:
+//     W_hk = 1/||rel_h - rel_k||  (0 when the distance is 0),  W_hh = 1
+//     d_h  = sum_k W_hk,  A = D^-1/2 (D - W) D^-1/2
+// One CTA walks scenes (grid-stride); each of its 8 warps owns one timestep slice.
+// Lanes own columns k; because W is symmetric the column sum a lane accumulates while
+// the warp walks the rows h = 0..N-1 IS the row sum d_k, in exactly the ascending order
+// scipy's csr mat-vec uses -- so no cross-lane reduction is needed at all and the fp64
+// mode reproduces networkx bit for bit.  Rows are written as coalesced 128-byte segments.
+//
+// Two arithmetic modes (template F64):
+//   F64  : dx,dy,dx^2,dy^2,+ in fp32 (separate roundings, as 0-dim fp32 torch tensors do),
+//          then sqrt, 1/x, row sum, ds = 1/sqrt(d) and ds_h*((D-W)_hk*ds_k) in fp64, cast
+//          to fp32 -- the reference's rounding points.
+//   fp32 : rsqrt on the same fp32 squared distance, 4-way split fp32 row sums; within
+//          ~3e-7 relative of the fp64 result (tests bound it at 2e-6; bar is 1e-5).
+#include "sstg_common.cuh"
+
+namespace sstg {
+
+namespace {
+
+constexpr int G_WARPS = 8;
+constexpr int G_THREADS = G_WARPS * 32;
+
+template <bool F64>
+struct RealT {
+  using type = float;
+};
+template <>
+struct RealT<true> {
+  using type = double;
+};
+
+// squared distance exactly as the reference: (x1-x2)**2 + (y1-y2)**2 on fp32 tensors
+__device__ __forceinline__ float sqdist(float xh, float yh, float xk, float yk) {
+  const float dx = __fsub_rn(xh, xk);
+  const float dy = __fsub_rn(yh, yk);
+  return __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
+}
+__device__ __forceinline__ double weight(float s, double) {
+  const double nrm = sqrt(static_cast<double>(s));  // math.sqrt (utils.py:24)
+  return nrm == 0.0 ? 0.0 : 1.0 / nrm;              // utils.py:25-27
+}
+__device__ __forceinline__ float weight(float s, float) { return s > 0.f ? rsqrtf(s) : 0.f; }
+
+template <bool F64, int NJ>
+__global__ void __launch_bounds__(G_THREADS)
+graph_build_kernel(const float* __restrict__ rel, const int32_t* __restrict__ seg_off,
+                   const int64_t* __restrict__ a_off, int S, int T, int NP, float* __restrict__ V,
+                   float* __restrict__ A, int flags) {
+  using Real = typename RealT<F64>::type;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float* xs = reinterpret_cast<float*>(smem_raw);  // [T][NP]
+  float* ys = xs + T * NP;                         // [T][NP]
+  Real* dsw = reinterpret_cast<Real*>(ys + T * NP) + (threadIdx.x >> 5) * NP;  // [warp][NP]
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const bool norm_lap = flags & SSTG_GRAPH_NORM_LAP;
+  const bool v_only = flags & SSTG_GRAPH_V_ONLY;
+
+  for (int s = blockIdx.x; s < S; s += gridDim.x) {
+    const int n0 = seg_off[s];
+    const int N = seg_off[s + 1] - n0;
+    const float* r = rel + static_cast<size_t>(n0) * 2 * T;
+    const int tot = N * 2 * T;
+    for (int i = tid; i < tot; i += G_THREADS) {  // (N,2,T) -> xs/ys[t][p]
+      const int p = i / (2 * T), rem = i - p * 2 * T;
+      const int c = rem / T, t = rem - c * T;
+      (c ? ys : xs)[t * NP + p] = r[i];
+    }
+    __syncthreads();
+    float2* Vs = reinterpret_cast<float2*>(V + static_cast<size_t>(n0) * T * 2);  // utils.py:42
+    for (int i = tid; i < N * T; i += G_THREADS) {
+      const int t = i / N, p = i - t * N;
+      Vs[i] = make_float2(xs[t * NP + p], ys[t * NP + p]);
+    }
+    if (!v_only) {
+      float* As = A + a_off[s];
+      for (int t = warp; t < T; t += G_WARPS) {
+        const float* xt = xs + t * NP;
+        const float* yt = ys + t * NP;
+        float xk[NJ], yk[NJ];
+        Real dsk[NJ];
+        Real lkk[NJ];  // (D - W)_kk = d_k - 1
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+          const int k = lane + 32 * j;
+          xk[j] = k < N ? xt[k] : 0.f;
+          yk[j] = k < N ? yt[k] : 0.f;
+        }
+        if (norm_lap) {
+          // ---- pass 1: d_k = sum_h W_hk (ascending h; W_kk = 1)
+          Real dk[NJ];
+          if (F64) {
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) dk[j] = Real(0);
+            for (int h = 0; h < N; ++h) {
+              const float xh = xt[h], yh = yt[h];
+#pragma unroll
+              for (int j = 0; j < NJ; ++j) {
+                Real w = weight(sqdist(xh, yh, xk[j], yk[j]), Real(0));
+                if (h == lane + 32 * j) w = Real(1);
+                dk[j] += w;
+              }
+            }
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) lkk[j] = dk[j] - Real(1);
+          } else {
+            Real acc[NJ][4];
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = Real(0);
+            int h = 0;
+            for (; h + 4 <= N; h += 4) {
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                const float xh = xt[h + u], yh = yt[h + u];
+#pragma unroll
+                for (int j = 0; j < NJ; ++j) acc[j][u] += weight(sqdist(xh, yh, xk[j], yk[j]), Real(0));
+              }
+            }
+            for (; h < N; ++h) {
+              const float xh = xt[h], yh = yt[h];
+#pragma unroll
+              for (int j = 0; j < NJ; ++j) acc[j][0] += weight(sqdist(xh, yh, xk[j], yk[j]), Real(0));
+            }
+            // the diagonal contributed w(0) = 0; d = 1 + off-diagonal sum
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) {
+              lkk[j] = (acc[j][0] + acc[j][1]) + (acc[j][2] + acc[j][3]);
+              dk[j] = Real(1) + lkk[j];
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < NJ; ++j) {
+            const int k = lane + 32 * j;
+            dsk[j] = F64 ? Real(1.0 / sqrt(static_cast<double>(dk[j]))) : Real(rsqrtf(static_cast<float>(dk[j])));
+            if (k < N) dsw[k] = dsk[j];
+          }
+          __syncwarp();
+        }
+        // ---- pass 2: A_hk = ds_h * ((D - W)_hk * ds_k), one coalesced row per iteration
+        float* At = As + static_cast<size_t>(t) * N * N;
+        for (int h = 0; h < N; ++h) {
+          const float xh = xt[h], yh = yt[h];
+          const Real dsh = norm_lap ? dsw[h] : Real(1);
+#pragma unroll
+          for (int j = 0; j < NJ; ++j) {
+            const int k = lane + 32 * j;
+            const Real w = weight(sqdist(xh, yh, xk[j], yk[j]), Real(0));
+            float a;
+            if (norm_lap) {
+              const Real l = (h == k) ? lkk[j] : -w;
+              a = static_cast<float>(dsh * (l * dsk[j]));
+              if (h != k && w == Real(0)) a = 0.f;  // absent edge: +0.0, not -0.0
+            } else {
+              a = (h == k) ? 1.f : static_cast<float>(w);
+            }
+            if (k < N) At[static_cast<size_t>(h) * N + k] = a;
+          }
+        }
+        __syncwarp();
+      }
+    }
+    __syncthreads();
+  }
+}
+
+template <bool F64, int NJ>
+int launch_nj(const float* rel, const int32_t* seg_off, const int64_t* a_off, int S, int T, int NP, float* V,
+              float* A, int flags, cudaStream_t st) {
+  const size_t smem = static_cast<size_t>(2 * T * NP) * sizeof(float) +
+                      static_cast<size_t>(G_WARPS * NP) * (F64 ? sizeof(double) : sizeof(float));
+  auto kern = graph_build_kernel<F64, NJ>;
+  if (smem > 48 * 1024)
+    SSTG_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)),
+                  "graph_build smem attr");
+  int dev = 0, sms = 148;
+  SSTG_CUDA_TRY(cudaGetDevice(&dev), "cudaGetDevice");
+  SSTG_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev), "sm count");
+  int per_sm = 1;
+  SSTG_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, G_THREADS, smem), "occupancy");
+  if (per_sm < 1) per_sm = 1;
+  const long long want = static_cast<long long>(sms) * per_sm;
+  const int grid = static_cast<int>(S < want ? S : want);
+  kern<<<grid, G_THREADS, smem, st>>>(rel, seg_off, a_off, S, T, NP, V, A, flags);
+  SSTG_CUDA_TRY(cudaGetLastError(), "graph_build launch");
+  return SSTG_OK;
+}
+
+template <bool F64>
+int launch_f(const float* rel, const int32_t* seg_off, const int64_t* a_off, int S, int T, int max_n, float* V,
+             float* A, int flags, cudaStream_t st) {
+  const int NP = (max_n + 3) & ~3;
+  if (max_n <= 32) return launch_nj<F64, 1>(rel, seg_off, a_off, S, T, NP, V, A, flags, st);
+  if (max_n <= 64) return launch_nj<F64, 2>(rel, seg_off, a_off, S, T, NP, V, A, flags, st);
+  if (max_n <= 128) return launch_nj<F64, 4>(rel, seg_off, a_off, S, T, NP, V, A, flags, st);
+  return launch_nj<F64, 8>(rel, seg_off, a_off, S, T, NP, V, A, flags, st);
+}
+
+}  // namespace
+
+int launch_graph_build(const float* rel, const int32_t* seg_off, const int64_t* a_off, int S, int T, int max_n,
+                       float* V, float* A, int flags, cudaStream_t st) {
+  if (S == 0) return SSTG_OK;
+  if (flags & SSTG_GRAPH_FP64) return launch_f<true>(rel, seg_off, a_off, S, T, max_n, V, A, flags, st);
+  return launch_f<false>(rel, seg_off, a_off, S, T, max_n, V, A, flags, st);
+}
+
+}  // namespace sstg

@@ -1,0 +1,129 @@
+// extern "C" surface of libsstg.so (declared in include/sstg.h): argument validation,
+// host-side planning, and dispatch to the kernel launchers.  No torch types, no
+// allocation, no synchronisation.
+#include <cstdio>
+#include <cstring>
+
+#include "sstg_common.cuh"
+
+namespace sstg {
+
+static thread_local char g_last_cuda_error[256] = "";
+
+void note_cuda_error(cudaError_t e, const char* where) {
+  std::snprintf(g_last_cuda_error, sizeof(g_last_cuda_error), "%s: %s (%s)", where, cudaGetErrorName(e),
+                cudaGetErrorString(e));
+}
+
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+}  // namespace sstg
+
+using namespace sstg;
+
+extern "C" {
+
+int sstg_version(void) { return 100; }
+
+const char* sstg_error_string(int code) {
+  switch (code) {
+    case SSTG_OK: return "ok";
+    case SSTG_EINVAL: return "invalid argument";
+    case SSTG_ETOOBIG: return "scene larger than SSTG_MAX_PEDS";
+    case SSTG_ECUDA: return "CUDA runtime error";
+    case SSTG_EARCH: return "device is not sm_100";
+    default: return "unknown error";
+  }
+}
+
+const char* sstg_last_cuda_error(void) { return g_last_cuda_error; }
+
+int sstg_plan_host(const int32_t* n_peds_host, int32_t S, int32_t T, int32_t* seg_off_host, int64_t* a_off_host,
+                   int32_t* tile_off_host, int32_t* n_tiles, int32_t* max_n, int64_t* a_floats) {
+  if (S < 0 || T <= 0 || (S > 0 && !n_peds_host) || !seg_off_host || !a_off_host || !tile_off_host || !n_tiles ||
+      !max_n || !a_floats)
+    return SSTG_EINVAL;
+  int64_t ped = 0, af = 0;
+  int32_t mx = 0, nt = 0, cols = 0, scenes = 0;
+  seg_off_host[0] = 0;
+  a_off_host[0] = 0;
+  tile_off_host[0] = 0;
+  for (int32_t s = 0; s < S; ++s) {
+    const int32_t n = n_peds_host[s];
+    if (n < 1) return SSTG_EINVAL;
+    if (n > SSTG_MAX_PEDS) return SSTG_ETOOBIG;
+    if (n > mx) mx = n;
+    // close the current TXP-CNN tile if this scene does not fit any more
+    if (scenes > 0 && (cols + n > SSTG_XTILE_COLS || scenes == SSTG_XTILE_MAX_SCENES)) {
+      tile_off_host[++nt] = s;
+      cols = 0;
+      scenes = 0;
+    }
+    cols += n;
+    ++scenes;
+    ped += n;
+    if (ped > INT32_MAX / 64) return SSTG_ETOOBIG;  // int32 element offsets inside the kernels
+    seg_off_host[s + 1] = static_cast<int32_t>(ped);
+    af += static_cast<int64_t>(T) * n * n;
+    af = (af + 3) & ~int64_t(3);  // every scene block starts 16-byte aligned
+    a_off_host[s + 1] = af;
+  }
+  if (S > 0) tile_off_host[++nt] = S;
+  *n_tiles = nt;
+  *max_n = mx;
+  *a_floats = af;
+  return SSTG_OK;
+}
+
+int sstg_graph_build(const float* rel, const int32_t* seg_off, const int64_t* a_off, int32_t S, int32_t T,
+                     int32_t max_n, float* V, float* A, int32_t flags, void* stream) {
+  const bool v_only = flags & SSTG_GRAPH_V_ONLY;
+  if (S < 0 || T <= 0 || T > 64 || max_n < 1) return SSTG_EINVAL;
+  if (max_n > SSTG_MAX_PEDS) return SSTG_ETOOBIG;
+  if (S == 0) return SSTG_OK;
+  if (!rel || !seg_off || !V || (!v_only && (!A || !a_off))) return SSTG_EINVAL;
+  if (!aligned16(V) || (!v_only && !aligned16(A))) return SSTG_EINVAL;
+  return launch_graph_build(rel, seg_off, a_off, S, T, max_n, V, A, flags, static_cast<cudaStream_t>(stream));
+}
+
+int sstg_stgcn_forward(const float* V, const float* A, const int32_t* seg_off, const int64_t* a_off, int32_t S,
+                       int32_t max_n, const float* params, const float* bn, float* H, int32_t sm_count,
+                       void* stream) {
+  if (S < 0 || max_n < 1) return SSTG_EINVAL;
+  if (max_n > SSTG_MAX_PEDS) return SSTG_ETOOBIG;
+  if (S == 0) return SSTG_OK;
+  if (!V || !A || !seg_off || !a_off || !params || !bn || !H) return SSTG_EINVAL;
+  if (!aligned16(V) || !aligned16(A) || !aligned16(H)) return SSTG_EINVAL;
+  return launch_stgcn_forward(V, A, seg_off, a_off, S, max_n, params, bn, H, sm_count,
+                              static_cast<cudaStream_t>(stream));
+}
+
+int sstg_txpcnn_forward(const float* H, const int32_t* seg_off, const int32_t* tile_off, int32_t n_tiles,
+                        int32_t max_n, const float* params, float* out, void* stream) {
+  if (n_tiles < 0 || max_n < 1) return SSTG_EINVAL;
+  if (max_n > SSTG_MAX_PEDS) return SSTG_ETOOBIG;
+  if (n_tiles == 0) return SSTG_OK;
+  if (!H || !seg_off || !tile_off || !params || !out) return SSTG_EINVAL;
+  return launch_txpcnn_forward(H, seg_off, tile_off, n_tiles, max_n, params, out,
+                               static_cast<cudaStream_t>(stream));
+}
+
+int sstg_nll_forward(const float* Vpred, const float* Vtr, const int32_t* seg_off, int32_t S, float* loss,
+                     void* stream) {
+  if (S < 0) return SSTG_EINVAL;
+  if (S == 0) return SSTG_OK;
+  if (!Vpred || !Vtr || !seg_off || !loss) return SSTG_EINVAL;
+  return launch_nll_forward(Vpred, Vtr, seg_off, S, loss, static_cast<cudaStream_t>(stream));
+}
+
+int sstg_sample_ade_fde(const float* Vpred, const float* Vtr, const float* last_obs, const int32_t* seg_off,
+                        int32_t S, int32_t total_peds, int32_t K, const float* eps, uint64_t seed, float* eps_out,
+                        double* min_ade, double* min_fde, float* pred_abs, int32_t flags, void* stream) {
+  if (S < 0 || total_peds < 0 || K < 1) return SSTG_EINVAL;
+  if (S == 0 || total_peds == 0) return SSTG_OK;
+  if (!Vpred || !Vtr || !last_obs || !seg_off || !min_ade || !min_fde) return SSTG_EINVAL;
+  return launch_sample_ade_fde(Vpred, Vtr, last_obs, seg_off, S, total_peds, K, eps, seed, eps_out, min_ade,
+                               min_fde, pred_abs, flags, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,271 @@
+"""Packed-batch host layer over the C ABI: plans, device buffers, and the
+inference pipeline  graph build -> st_gcn -> TXP-CNN -> K-sample ADE/FDE.
+
+torch is used for device memory, streams and (in `parallel.py`) torch.distributed
+only; every arithmetic step is a libsstg.so kernel.  The layouts are the
+reference's own: pedestrians packed as `TrajectoryDataset.obs_traj_rel` packs them
+(utils.py:180-190), per-scene V (T,N,2), A (T,N,N), V_pred (5,12,N).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Dict, Optional
+
+import numpy as np
+import torch
+
+from . import _lib as L
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _stream(dev: torch.device):
+    return torch.cuda.current_stream(dev).cuda_stream
+
+
+def _need(t: torch.Tensor, dtype, what: str, dev=None):
+    if not isinstance(t, torch.Tensor) or t.dtype != dtype:
+        raise TypeError(f"{what} must be a {dtype} tensor")
+    if not t.is_cuda:
+        raise RuntimeError(f"{what} must live on a CUDA device (no CPU fallback)")
+    if dev is not None and t.device != dev:
+        raise RuntimeError(f"{what} is on {t.device}, expected {dev}")
+    if not t.is_contiguous():
+        raise RuntimeError(f"{what} must be contiguous")
+    return t
+
+
+class ScenePlan:
+    """Host-side description of a ragged batch of scenes (sstg_plan_host)."""
+
+    def __init__(self, n_peds, T: int = L.T_OBS):
+        n = np.ascontiguousarray(np.asarray(n_peds, dtype=np.int32).reshape(-1))
+        S = int(n.size)
+        self.S, self.T = S, int(T)
+        self.n_peds = n
+        self.seg_off = np.zeros(S + 1, np.int32)
+        self.a_off = np.zeros(S + 1, np.int64)
+        self.tile_off = np.zeros(S + 1, np.int32)
+        nt, mx, af = np.zeros(1, np.int32), np.zeros(1, np.int32), np.zeros(1, np.int64)
+        lib = L.load()
+        L.check(lib.sstg_plan_host(n.ctypes.data, S, self.T, self.seg_off.ctypes.data, self.a_off.ctypes.data,
+                                   self.tile_off.ctypes.data, nt.ctypes.data, mx.ctypes.data, af.ctypes.data),
+                "sstg_plan_host")
+        self.n_tiles, self.max_n, self.a_floats = int(nt[0]), int(mx[0]), int(af[0])
+        self.tile_off = self.tile_off[: self.n_tiles + 1].copy()
+        self.P = int(self.seg_off[-1])
+        self._dev: Dict[torch.device, "DevicePlan"] = {}
+
+    def on(self, device) -> "DevicePlan":
+        device = torch.device(device)
+        if device.type != "cuda":
+            raise RuntimeError("ScenePlan.on(): a CUDA device is required (no CPU fallback)")
+        if device.index is None:
+            device = torch.device("cuda", torch.cuda.current_device())
+        if device not in self._dev:
+            self._dev[device] = DevicePlan(
+                self, device,
+                torch.from_numpy(self.seg_off).to(device),
+                torch.from_numpy(self.a_off).to(device),
+                torch.from_numpy(self.tile_off).to(device))
+        return self._dev[device]
+
+
+@dataclass
+class DevicePlan:
+    host: ScenePlan
+    device: torch.device
+    seg_off: torch.Tensor
+    a_off: torch.Tensor
+    tile_off: torch.Tensor
+
+
+# --------------------------------------------------------------------------
+# functional ops (device tensors in, device tensors out; `out=` to reuse buffers)
+# --------------------------------------------------------------------------
+def graph_build(dp: DevicePlan, rel: torch.Tensor, T: int, *, norm_lap: bool = True, fp64: bool = False,
+                v_only: bool = False, V: Optional[torch.Tensor] = None, A: Optional[torch.Tensor] = None):
+    """utils.seq_to_graph (utils.py:29-53) for every scene of the packed batch.
+    rel: [P, 2, T] fp32.  Returns (V packed (T,N,2) blocks, A packed (T,N,N) blocks or None)."""
+    h, dev = dp.host, dp.device
+    _need(rel, torch.float32, "rel", dev)
+    if tuple(rel.shape) != (h.P, 2, T):
+        raise ValueError(f"rel must be [{h.P}, 2, {T}], got {tuple(rel.shape)}")
+    if not v_only and T != h.T:
+        raise ValueError(f"plan was made for T={h.T}; build a ScenePlan(n_peds, T={T}) for this adjacency")
+    if V is None:
+        V = torch.empty(h.P * T * 2, dtype=torch.float32, device=dev)
+    if A is None and not v_only:
+        A = torch.empty(h.a_floats, dtype=torch.float32, device=dev)
+    flags = (L.GRAPH_NORM_LAP if norm_lap else 0) | (L.GRAPH_FP64 if fp64 else 0) | (L.GRAPH_V_ONLY if v_only else 0)
+    with torch.cuda.device(dev):
+        L.check(L.load().sstg_graph_build(_ptr(rel), _ptr(dp.seg_off), _ptr(dp.a_off), h.S, T, h.max_n,
+                                          _ptr(V), _ptr(A), flags, _stream(dev)), "sstg_graph_build")
+    return V, (None if v_only else A)
+
+
+def stgcn_forward(dp: DevicePlan, V, A, params, bn, *, H=None, sm_count: int = 0):
+    """st_gcn.forward (model.py:145-155), eval-mode BN, for the packed batch -> H (5,8,N) blocks."""
+    h, dev = dp.host, dp.device
+    for t, w in ((V, "V"), (A, "A"), (params, "params"), (bn, "bn")):
+        _need(t, torch.float32, w, dev)
+    if params.numel() != L.N_PARAMS or bn.numel() != L.N_BN:
+        raise ValueError("params must hold 7563 floats and bn 30 floats")
+    if V.numel() < h.P * L.T_OBS * 2 or A.numel() < h.a_floats:
+        raise ValueError("V / A buffers are smaller than the plan requires")
+    if h.T != L.T_OBS:
+        raise AssertionError(f"A.size(0) must equal the st_gcn kernel size {L.T_OBS}")  # model.py:65
+    if H is None:
+        H = torch.empty(h.P * 40, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        L.check(L.load().sstg_stgcn_forward(_ptr(V), _ptr(A), _ptr(dp.seg_off), _ptr(dp.a_off), h.S, h.max_n,
+                                            _ptr(params), _ptr(bn), _ptr(H), sm_count, _stream(dev)),
+                "sstg_stgcn_forward")
+    return H
+
+
+def txpcnn_forward(dp: DevicePlan, H, params, *, out=None):
+    """model.py:187-195 for the packed batch -> V_pred (5,12,N) blocks."""
+    h, dev = dp.host, dp.device
+    _need(H, torch.float32, "H", dev)
+    _need(params, torch.float32, "params", dev)
+    if out is None:
+        out = torch.empty(h.P * 60, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        L.check(L.load().sstg_txpcnn_forward(_ptr(H), _ptr(dp.seg_off), _ptr(dp.tile_off), h.n_tiles, h.max_n,
+                                             _ptr(params), _ptr(out), _stream(dev)), "sstg_txpcnn_forward")
+    return out
+
+
+def nll_forward(dp: DevicePlan, Vpred, Vtr, *, loss=None):
+    """metrics.bivariate_loss (metrics.py:84-113) per scene -> loss[S]."""
+    h, dev = dp.host, dp.device
+    _need(Vpred, torch.float32, "Vpred", dev)
+    _need(Vtr, torch.float32, "Vtr", dev)
+    if loss is None:
+        loss = torch.empty(h.S, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        L.check(L.load().sstg_nll_forward(_ptr(Vpred), _ptr(Vtr), _ptr(dp.seg_off), h.S, _ptr(loss), _stream(dev)),
+                "sstg_nll_forward")
+    return loss
+
+
+def sample_ade_fde(dp: DevicePlan, Vpred, Vtr, last_obs, K: int = 20, *, eps=None, seed: int = 0,
+                   want_eps: bool = False, want_pred: bool = False, fp64_dist: bool = True,
+                   min_ade=None, min_fde=None):
+    """test.py:59-123 for the packed batch.  Returns dict(min_ade[P] f64, min_fde[P] f64,
+    eps (noise used, if want_eps), pred_abs (K,12,N,2 blocks, if want_pred))."""
+    h, dev = dp.host, dp.device
+    for t, w in ((Vpred, "Vpred"), (Vtr, "Vtr"), (last_obs, "last_obs")):
+        _need(t, torch.float32, w, dev)
+    if last_obs.numel() != h.P * 2:
+        raise ValueError("last_obs must be [P, 2]")
+    n_eps = h.P * K * L.T_PRED * 2
+    if eps is not None:
+        _need(eps, torch.float32, "eps", dev)
+        if eps.numel() != n_eps:
+            raise ValueError(f"eps must hold {n_eps} floats ((K,12,N,2) per scene)")
+    if min_ade is None:
+        min_ade = torch.empty(h.P, dtype=torch.float64, device=dev)
+    if min_fde is None:
+        min_fde = torch.empty(h.P, dtype=torch.float64, device=dev)
+    eps_out = torch.empty(n_eps, dtype=torch.float32, device=dev) if want_eps else None
+    pred = torch.empty(n_eps, dtype=torch.float32, device=dev) if want_pred else None
+    with torch.cuda.device(dev):
+        L.check(L.load().sstg_sample_ade_fde(_ptr(Vpred), _ptr(Vtr), _ptr(last_obs), _ptr(dp.seg_off), h.S, h.P, K,
+                                             _ptr(eps), seed & (2 ** 64 - 1), _ptr(eps_out), _ptr(min_ade),
+                                             _ptr(min_fde), _ptr(pred), L.EVAL_FP64_DIST if fp64_dist else 0,
+                                             _stream(dev)), "sstg_sample_ade_fde")
+    return {"min_ade": min_ade, "min_fde": min_fde, "eps": eps_out, "pred_abs": pred}
+
+
+# --------------------------------------------------------------------------
+# the inference pipeline
+# --------------------------------------------------------------------------
+class InferenceEngine:
+    """Weights resident on one GPU + reusable workspaces; runs the whole hot path
+    on a packed batch: seq_to_graph -> social_stgcnn.forward (eval) -> test()'s
+    K-sample ADE/FDE.  `graph_fp64` / `fp64_dist` select the reference's fp64
+    rounding islands (bit-level parity) or the fp32 fast path (within 1e-5)."""
+
+    def __init__(self, params, bn, device="cuda"):
+        device = torch.device(device)
+        if device.type != "cuda":
+            raise RuntimeError("InferenceEngine needs a CUDA device (no CPU fallback)")
+        if device.index is None:
+            device = torch.device("cuda", torch.cuda.current_device())
+        L.load()
+        self.device = device
+        self.params = torch.as_tensor(np.asarray(params, np.float32)).reshape(-1).to(device).contiguous()
+        self.bn = torch.as_tensor(np.asarray(bn, np.float32)).reshape(-1).to(device).contiguous()
+        if self.params.numel() != L.N_PARAMS or self.bn.numel() != L.N_BN:
+            raise ValueError("params must hold 7563 floats and bn 30 floats")
+        self._ws: Dict[tuple, Dict[str, torch.Tensor]] = {}
+        self._pin: Dict[tuple, Dict[str, torch.Tensor]] = {}
+
+    def workspace(self, plan: ScenePlan) -> Dict[str, torch.Tensor]:
+        key = (plan.S, plan.P, plan.a_floats)
+        ws = self._ws.get(key)
+        if ws is None:
+            d, f = self.device, torch.float32
+            ws = {
+                "V_obs": torch.empty(plan.P * L.T_OBS * 2, dtype=f, device=d),
+                "A_obs": torch.empty(plan.a_floats, dtype=f, device=d),
+                "V_tr": torch.empty(plan.P * L.T_PRED * 2, dtype=f, device=d),
+                "H": torch.empty(plan.P * 40, dtype=f, device=d),
+                "V_pred": torch.empty(plan.P * 60, dtype=f, device=d),
+                "min_ade": torch.empty(plan.P, dtype=torch.float64, device=d),
+                "min_fde": torch.empty(plan.P, dtype=torch.float64, device=d),
+            }
+            self._ws = {key: ws}  # keep one workspace alive
+        return ws
+
+    def infer(self, plan: ScenePlan, obs_rel, pred_rel, last_obs, K: int = 20, *, eps=None, seed: int = 0,
+              graph_fp64: bool = False, fp64_dist: bool = False, want_eps: bool = False, want_pred: bool = False):
+        """Device-resident inputs: obs_rel [P,2,8], pred_rel [P,2,12], last_obs [P,2].
+        Returns the workspace dict (views valid until the next call) plus eps / pred_abs."""
+        dp = plan.on(self.device)
+        ws = self.workspace(plan)
+        graph_build(dp, obs_rel, L.T_OBS, fp64=graph_fp64, V=ws["V_obs"], A=ws["A_obs"])
+        graph_build(dp, pred_rel, L.T_PRED, v_only=True, V=ws["V_tr"])
+        stgcn_forward(dp, ws["V_obs"], ws["A_obs"], self.params, self.bn, H=ws["H"])
+        txpcnn_forward(dp, ws["H"], self.params, out=ws["V_pred"])
+        r = sample_ade_fde(dp, ws["V_pred"], ws["V_tr"], last_obs, K, eps=eps, seed=seed, want_eps=want_eps,
+                           want_pred=want_pred, fp64_dist=fp64_dist, min_ade=ws["min_ade"], min_fde=ws["min_fde"])
+        out = dict(ws)
+        out["eps"], out["pred_abs"] = r["eps"], r["pred_abs"]
+        return out
+
+    def infer_host(self, plan: ScenePlan, obs_rel, pred_rel, last_obs, K: int = 20, **kw):
+        """End-to-end call with HOST buffers (numpy or CPU tensors, ideally pinned):
+        H2D copies, the pipeline, and the D2H copy of the per-pedestrian minima.
+        Returns (min_ade, min_fde) as numpy float64 arrays of length P."""
+        key = (plan.P,)
+        pin = self._pin.get(key)
+        if pin is None:
+            d = self.device
+            pin = {
+                "d_obs": torch.empty(plan.P, 2, L.T_OBS, dtype=torch.float32, device=d),
+                "d_pred": torch.empty(plan.P, 2, L.T_PRED, dtype=torch.float32, device=d),
+                "d_last": torch.empty(plan.P, 2, dtype=torch.float32, device=d),
+                "h_out": torch.empty(2, plan.P, dtype=torch.float64).pin_memory(),
+            }
+            self._pin = {key: pin}
+        pin["d_obs"].copy_(torch.as_tensor(obs_rel), non_blocking=True)
+        pin["d_pred"].copy_(torch.as_tensor(pred_rel), non_blocking=True)
+        pin["d_last"].copy_(torch.as_tensor(last_obs), non_blocking=True)
+        out = self.infer(plan, pin["d_obs"], pin["d_pred"], pin["d_last"], K, **kw)
+        pin["h_out"][0].copy_(out["min_ade"], non_blocking=True)
+        pin["h_out"][1].copy_(out["min_fde"], non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        return pin["h_out"][0].numpy(), pin["h_out"][1].numpy()
+
+    @staticmethod
+    def h2d_bytes(plan: ScenePlan) -> int:
+        return plan.P * (2 * L.T_OBS + 2 * L.T_PRED + 2) * 4
+
+    @staticmethod
+    def d2h_bytes(plan: ScenePlan) -> int:
+        return plan.P * 2 * 8
