@@ -1,0 +1,347 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the Social-STGCNN hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P bench.py --gpus N --steps K --warmup W
+
+Metric (BASELINE.json): scenes/sec of  graph build + ST-GCN/TXP-CNN forward + 20-sample
+ADE/FDE  on synthetic dense crowds (64 pedestrians per scene, obs 8 -> pred 12), sharded by
+scene across the GPUs with no data-path collective (weak scaling: a fixed shard per GPU).
+One "step" = one pass of the whole hot path over this rank's resident batch of scenes.
+
+The JSON line carries: `value` (device-resident inputs), `e2e` (host buffers, H2D + D2H in
+the timed region, through InferenceEngine.infer_host), `roofline` for the st_gcn kernel (the
+kernel BASELINE.json states the HBM target on) plus `kernels` with every kernel's share,
+`cpu_baseline` (the oracle port timed on the host cores, rank 0 / N=1 only), `clocks`.
+
+`--impl reference` times the reference's CPU algorithm (oracle port -- the Python reference
+itself cannot travel to the GPU box) with all host cores on a bounded sample per step.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "scenes_per_sec_graph_fwd_ade_fde"
+UNIT = "scenes/s"
+N_PEDS = 64
+K_SAMPLES = 20
+
+
+def synth_batch(num_scenes, n_peds, seed):
+    """Synthetic crowds of SURVEY 8(d): random starts in (-10,10)^2, per-pedestrian velocity
+    U(-.5,.5)^2 + N(0, .1^2) per frame, positions rounded to 4 decimals, rel = first
+    difference with rel[:, :, 0] = 0 (utils.py:145,153-155).  Built with torch on the CPU."""
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    P = num_scenes * n_peds
+    start = torch.rand(P, 2, generator=g) * 20 - 10
+    vel = torch.rand(P, 2, generator=g) - 0.5
+    steps = vel[:, :, None] + 0.1 * torch.randn(P, 2, 20, generator=g)
+    steps[:, :, 0] = 0
+    pos = torch.round((start[:, :, None] + torch.cumsum(steps, 2)) * 1e4) / 1e4
+    rel = torch.zeros_like(pos)
+    rel[:, :, 1:] = pos[:, :, 1:] - pos[:, :, :-1]
+    return (rel[:, :, :8].contiguous(), rel[:, :, 8:].contiguous(), pos[:, :, 7].contiguous())
+
+
+def load_weights():
+    w = np.load(os.path.join(ROOT, "tests", "golden", "weights.npz"))
+    return w["eth.params"], w["eth.bn"]
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock + throttle reasons of one GPU through NVML while the timed region runs."""
+    BITS = {0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x10: "sync_boost",
+            0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown", 0x80: "hw_power_brake_slowdown",
+            0x100: "display_clock_setting"}
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.stop_flag, self.sm, self.reasons, self.max_mhz = index, False, [], set(), None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        while not self.stop_flag:
+            try:
+                self.sm.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                r = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                for bit, name in self.BITS.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.02)
+
+    def result(self):
+        return {"sm_mhz": (float(np.median(self.sm)) if self.sm else None), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.sm)}
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ---------------------------------------------------------------------------------
+# CPU legs: the oracle port (the checker) timed on host cores
+# ---------------------------------------------------------------------------------
+def _cpu_worker(args):
+    import torch
+    torch.set_num_threads(1)
+    from oracle import stgcnn_oracle as O
+    params, bn, obs_rel, pred_rel, last, n_peds, seed = args
+    P_, S_ = O.unflatten_params(params), O.unflatten_bn(bn)
+    g = torch.Generator().manual_seed(seed)
+    n_sc = obs_rel.shape[0] // n_peds
+    tot = 0.0
+    for i in range(n_sc):
+        sl = slice(i * n_peds, (i + 1) * n_peds)
+        eps = torch.randn(K_SAMPLES, 12, n_peds, 2, generator=g).numpy()       # the reference draws its own noise
+        a, f = O.infer_scene(P_, S_, obs_rel[sl], pred_rel[sl], last[sl], eps)
+        tot += float(a.sum() + f.sum())
+    return n_sc, tot
+
+
+def cpu_port_throughput(n_scenes, procs, seed=0):
+    """scenes/s of the oracle port (graph build + eval forward + 20-sample ADE/FDE, batch 1
+    per scene as the reference does) using `procs` host processes."""
+    import multiprocessing as mp
+    params, bn = load_weights()
+    obs_rel, pred_rel, last = [t.numpy() for t in synth_batch(n_scenes, N_PEDS, 4321 + seed)]
+    per = max(1, n_scenes // procs)
+    jobs = []
+    for w in range(procs):
+        lo, hi = w * per * N_PEDS, (w + 1) * per * N_PEDS
+        if lo >= obs_rel.shape[0]:
+            break
+        jobs.append((params, bn, obs_rel[lo:hi], pred_rel[lo:hi], last[lo:hi], N_PEDS, seed + w))
+    t0 = time.perf_counter()
+    if procs == 1:
+        res = [_cpu_worker(jobs[0])]
+    else:
+        with mp.get_context("fork").Pool(len(jobs)) as pool:
+            res = pool.map(_cpu_worker, jobs)
+    dt = time.perf_counter() - t0
+    done = sum(r[0] for r in res)
+    return done / dt, done, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    per_step = 256 * cores          # ~2-3 s of CPU work per step on all cores
+    for _ in range(args.warmup):
+        cpu_port_throughput(cores, cores)
+    t0 = time.perf_counter()
+    done = 0
+    for s in range(args.steps):
+        _, d, _ = cpu_port_throughput(per_step, cores, seed=s)
+        done += d
+    dt = time.perf_counter() - t0
+    v = done / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / max(1, args.steps), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"synthetic dense crowds, {N_PEDS} peds/scene, obs 8 -> pred 12, K={K_SAMPLES}; "
+                               f"bounded sample of {per_step} scenes per step"},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{done} scenes in {dt:.1f}s, oracle port (vectorised numpy graph build + torch "
+                                   f"CPU fp32 forward + numpy sampling), one process per core"},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import social_stgcnn_b200 as sstg
+    from social_stgcnn_b200 import engine as E
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device; there is no CPU fallback for the product path")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    S, N = args.scenes_per_gpu, N_PEDS
+    params, bn = load_weights()
+    eng = sstg.InferenceEngine(params, bn, dev)
+    plan = sstg.ScenePlan(np.full(S, N, np.int32))
+    obs_h, pred_h, last_h = synth_batch(S, N, 1234 + rank)          # this rank's shard
+    obs_h, pred_h, last_h = obs_h.pin_memory(), pred_h.pin_memory(), last_h.pin_memory()
+    obs, pred, last = obs_h.to(dev), pred_h.to(dev), last_h.to(dev)
+    dp = plan.on(dev)
+    ws = eng.workspace(plan)
+    names = ["graph_build", "graph_v_tr", "stgcn_forward", "txpcnn_forward", "sample_ade_fde"]
+
+    def step(ev=None):
+        def mark(i):
+            if ev is not None:
+                ev[i].record()
+        mark(0)
+        E.graph_build(dp, obs, 8, V=ws["V_obs"], A=ws["A_obs"])
+        mark(1)
+        E.graph_build(dp, pred, 12, v_only=True, V=ws["V_tr"])
+        mark(2)
+        E.stgcn_forward(dp, ws["V_obs"], ws["A_obs"], eng.params, eng.bn, H=ws["H"])
+        mark(3)
+        E.txpcnn_forward(dp, ws["H"], eng.params, out=ws["V_pred"])
+        mark(4)
+        E.sample_ade_fde(dp, ws["V_pred"], ws["V_tr"], last, K_SAMPLES, seed=args.seed, fp64_dist=False,
+                         min_ade=ws["min_ade"], min_fde=ws["min_fde"])
+        mark(5)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(6)] for _ in range(args.steps)]
+    t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t_start.record()
+    for k in range(args.steps):
+        step(evs[k])
+    t_end.record()
+    barrier()
+    sampler.stop_flag = True
+    ms_total = t_start.elapsed_time(t_end)
+    kern_ms = {n: float(np.mean([evs[k][i].elapsed_time(evs[k][i + 1]) for k in range(args.steps)]))
+               for i, n in enumerate(names)}
+    sum_a, sum_f = float(ws["min_ade"].sum()), float(ws["min_fde"].sum())
+
+    # ---- e2e: host buffers -> H2D -> pipeline -> D2H, through the public API
+    for _ in range(max(1, min(2, args.warmup))):
+        eng.infer_host(plan, obs_h, pred_h, last_h, K_SAMPLES, seed=args.seed)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        a_h, f_h = eng.infer_host(plan, obs_h, pred_h, last_h, K_SAMPLES, seed=args.seed)
+    e1.record()
+    barrier()
+    ms_e2e = e0.elapsed_time(e1)
+
+    t = torch.tensor([ms_total, ms_e2e], dtype=torch.float64, device=dev)
+    red = torch.tensor([sum_a, sum_f, float(plan.P)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)          # max over ranks
+        dist.all_reduce(red, op=dist.ReduceOp.SUM)        # dataset-level ADE/FDE: the only exchange, outside timing
+    ms_total, ms_e2e = float(t[0]), float(t[1])
+    if rank == 0:
+        peak, peak_src = measured_peak_gbs()
+        total_scenes = S * world * args.steps
+        value = total_scenes / (ms_total * 1e-3)
+        sg = kern_ms["stgcn_forward"]
+        bytes_s = (64 * N + 32 * N * N + 160 * N) * S            # SURVEY 8(d) row "S", per launch
+        achieved = bytes_s / (sg * 1e-3) / 1e9
+        ksum = sum(kern_ms.values())
+        alg = {"graph_build": (128 * N + 32 * N * N) * S, "graph_v_tr": 192 * N * S, "stgcn_forward": bytes_s,
+               "txpcnn_forward": 400 * N * S, "sample_ade_fde": 352 * N * S}
+        kernels = {n: {"ms": round(kern_ms[n], 4), "share": round(kern_ms[n] / ksum, 4),
+                       "GBps": round(alg[n] / (kern_ms[n] * 1e-3) / 1e9, 1)} for n in names}
+        kernels["txpcnn_forward"]["TFLOPs_fp32"] = round(60480 * N * S / (kern_ms["txpcnn_forward"] * 1e-3) / 1e12, 2)
+        kernels["txpcnn_forward"]["bound"] = "fp32 FMA (not HBM, not tensor): 60,480 flop/ped-column vs 400 B"
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"synthetic dense crowds: {S} scenes/GPU x {N} peds (config 3: 1M scenes at 8 GPUs "
+                                   f"with the default shard), obs 8 -> pred 12, K={K_SAMPLES} Philox samples, "
+                                   f"eth checkpoint weights",
+                       "scenes_per_gpu": S, "peds_per_scene": N, "ksteps": K_SAMPLES, "graph_mode": "fp32",
+                       "l2_policy": "inputs larger than L2 (A is %.1f GB per step)" % (plan.a_floats * 4 / 1e9),
+                       "parallelism": f"scene-sharded x{world}, no data-path collective"},
+            "roofline": {"kernel": "stgcn_fwd_kernel", "bound": "hbm", "achieved": achieved, "peak": peak,
+                         "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "share_of_step": kern_ms["stgcn_forward"] / ksum},
+            "kernels": kernels,
+            "e2e": {"value": S * world * args.steps / (ms_e2e * 1e-3), "unit": UNIT,
+                    "h2d_bytes_per_step": eng.h2d_bytes(plan), "d2h_bytes_per_step": eng.d2h_bytes(plan)},
+            "gpu_launches": 5 * args.steps,
+            "clocks": sampler.result(),
+            "result": {"ade": red[0].item() / red[2].item(), "fde": red[1].item() / red[2].item(),
+                       "peds": int(red[2].item())},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            cores = os.cpu_count() or 1
+            v1, d1, t1 = cpu_port_throughput(max(4, cores), 1)      # calibrate
+            n = int(max(cores, min(4096, 12.0 * v1 * cores)))
+            v, done, dt = cpu_port_throughput(n, cores)
+            ref_t = ""
+            p = os.path.join(ROOT, "tests", "golden", "REFERENCE_TIMING.txt")
+            if os.path.exists(p):
+                ref_t = " | " + open(p).read().strip()
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                                    "sample": f"{done} scenes of {N} peds in {dt:.1f}s, oracle port, one process per "
+                                              f"core (single process: {v1:.1f} scenes/s){ref_t}"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--scenes-per-gpu", type=int, default=131072)
+    ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+    if args.gpus > 1 and "RANK" not in os.environ:
+        # convenience: re-launch ourselves under torchrun, one rank per GPU
+        import subprocess
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", "29511", os.path.abspath(__file__)] + sys.argv[1:]
+        sys.exit(subprocess.call(cmd))
+    run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -255,7 +255,7 @@ def train_step(P, S, scenes, batch_size):
         if i == len(scenes) - 1:
             break
         l = bivariate_loss(vpred_tn5(out), torch.as_tensor(Vt, dtype=out.dtype))
-        per_scene.append(float(l))
+        per_scene.append(float(l.detach()))
         total = l if total is None else total + l
     loss = total / batch_size
     loss.backward()
