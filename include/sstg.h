@@ -40,6 +40,9 @@ extern "C" {
 #define SSTG_MAX_PEDS 256  /* largest scene the kernels accept (shared-memory bound) */
 #define SSTG_XTILE_COLS 128 /* TXP-CNN tile: whole scenes up to this many pedestrian columns */
 #define SSTG_XTILE_MAX_SCENES 32
+#define SSTG_ST_PARAMS 142          /* st_gcn parameters: the first 142 floats of the block */
+#define SSTG_TXP_GRAD_STRIDE 7424   /* row length of the TXP-CNN partial-gradient buffer (7421 padded) */
+#define SSTG_SAVE_FLOATS_PER_PED 600 /* activations kept for backward: Y 40, Z 40, H 40, U 4x60, X 4x60 */
 
 /* flags of sstg_graph_build */
 #define SSTG_GRAPH_NORM_LAP 1 /* norm_lap_matr=True (utils.py:48-50) */
@@ -129,6 +132,64 @@ int sstg_sample_ade_fde(const float* Vpred, const float* Vtr, const float* last_
                         const float* eps, uint64_t seed, float* eps_out,
                         double* min_ade, double* min_fde, float* pred_abs,
                         int32_t flags, void* stream);
+
+/* ---- stand-alone trajectory helpers (the reference's metrics.py API) ------------------
+ * sstg_rel_to_abs: metrics.nodes_rel_to_nodes_abs (metrics.py:69-75) for packed (T,N_s,2)
+ * blocks (scene s at float offset seg_off[s]*T*2): out[t,p] = init[p] + sum_{u<=t} rel[u,p]
+ * with the reference's rounding points.  init [P,2] float64 (the reference passes a float64 array). */
+int sstg_rel_to_abs(const float* rel, const double* init, const int32_t* seg_off, int32_t S,
+                    int32_t total_peds, int32_t T, float* out, void* stream);
+
+/* sstg_traj_error: the inner sums of metrics.ade / metrics.fde (metrics.py:21-53) per
+ * pedestrian for packed (T,N_s,2) blocks: sum_dist[p] = sum_t ||pred - tgt|| (fp64),
+ * final_dist[p] = ||pred - tgt|| at t = T-1. */
+int sstg_traj_error(const float* pred, const float* tgt, const int32_t* seg_off, int32_t S,
+                    int32_t total_peds, int32_t T, double* sum_dist, double* final_dist, void* stream);
+
+/* ===================== training path (train.py:28-79) =================================
+ * The reference trains with batch 1 and accumulates the loss of `batch_size` scenes before
+ * one backward (train.py:58-74).  A packed batch reproduces that exactly: BatchNorm uses
+ * the statistics of each scene separately (train mode, model.py:114,121,141), the loss
+ * weights carry the 1/batch_size and the "last scene of the group is not scored" rule
+ * (train.py:58-66), and the gradient of the whole group comes out of one backward. */
+
+/* Rows of the two partial-gradient buffers sstg_backward needs for a batch of S scenes in
+ * n_tiles TXP-CNN tiles on the current device: partial_st[rows_st][SSTG_ST_PARAMS],
+ * partial_tx[rows_tx][SSTG_TXP_GRAD_STRIDE]. */
+int sstg_train_partial_rows(int32_t S, int32_t n_tiles, int32_t* rows_st, int32_t* rows_tx);
+
+/* social_stgcnn.forward in TRAIN mode (model.py:182-198 with nn.BatchNorm2d batch statistics).
+ *   save         [total_peds * SSTG_SAVE_FLOATS_PER_PED] activations for sstg_backward
+ *   scene_stats  [S][30]  per scene: mean,var(biased) of BN tcn.0, tcn.3, residual.1
+ *   Vpred        (5,12,N_s) blocks like sstg_txpcnn_forward */
+int sstg_forward_train(const float* V, const float* A, const int32_t* seg_off, const int64_t* a_off,
+                       const int32_t* tile_off, int32_t S, int32_t n_tiles, int32_t max_n, int32_t total_peds,
+                       const float* params, float* save, float* scene_stats, float* Vpred, void* stream);
+
+/* BatchNorm running statistics after forwarding the S scenes in order (momentum 0.1, unbiased
+ * variance -- torch.nn.BatchNorm2d as used at model.py:114,121,141).  bn[30] is updated in place. */
+int sstg_bn_running_update(const float* scene_stats, const int32_t* seg_off, int32_t S, double momentum,
+                           float* bn, void* stream);
+
+/* metrics.bivariate_loss forward + its gradient (metrics.py:84-113 under autograd):
+ *   loss[s]   per-scene mean NLL;   dVpred = scene_weight[s] * d loss[s] / d Vpred  ((5,12,N_s) blocks)
+ *   scene_weight may be NULL (= 1).  For train.py's accumulation: 1/batch_size, 0 for the last
+ *   scene of each optimiser group (train.py:58-66). */
+int sstg_nll_backward(const float* Vpred, const float* Vtr, const int32_t* seg_off, int32_t S,
+                      const float* scene_weight, float* loss, float* dVpred, void* stream);
+
+/* Backward of the whole model (loss.backward(), train.py:67): from dVpred to the flat gradient
+ * grad[SSTG_N_PARAMS] in named_parameters() order (zeros for tpcnns.4 / prelus.4, which
+ * model.py:191 never executes).  dH_ws [total_peds*40] is scratch.  Deterministic: no atomics. */
+int sstg_backward(const float* V, const float* A, const int32_t* seg_off, const int64_t* a_off,
+                  const int32_t* tile_off, int32_t S, int32_t n_tiles, int32_t max_n, int32_t total_peds,
+                  const float* params, const float* save, const float* scene_stats, const float* dVpred,
+                  float* dH_ws, float* partial_st, float* partial_tx, float* grad, void* stream);
+
+/* optimizer.step() of train.py:197 (SGD, lr only) with the optional clip_grad_norm_ of
+ * train.py:69-70 (clip_norm <= 0: off).  grad_norm_out (1 float, may be NULL) gets ||grad||_2. */
+int sstg_sgd_step(float* params, const float* grad, int32_t n, float lr, float clip_norm,
+                  float* grad_norm_out, void* stream);
 
 #ifdef __cplusplus
 }

@@ -15,6 +15,7 @@ LIB_PATH = os.path.join(_PKG, "libsstg.so")
 T_OBS, T_PRED, C_IN, C_OUT = 8, 12, 2, 5
 N_PARAMS, N_BN, MAX_PEDS = 7563, 30, 256
 XTILE_COLS, XTILE_MAX_SCENES = 128, 32
+ST_PARAMS, TXP_GRAD_STRIDE, SAVE_FLOATS_PER_PED = 142, 7424, 600
 GRAPH_NORM_LAP, GRAPH_FP64, GRAPH_V_ONLY = 1, 2, 4
 EVAL_FP64_DIST = 1
 
@@ -31,11 +32,17 @@ _SIGS = {
     "sstg_nll_forward": (C.c_int, [_p, _p, _p, _i32, _p, _p]),
     "sstg_sample_ade_fde": (C.c_int, [_p, _p, _p, _p, _i32, _i32, _i32, _p, _u64, _p, _p, _p, _p, _i32, _p]),
 }
-# entry points added by later kernels; bound only if the library exports them
-_OPTIONAL_SIGS = {
-    "sstg_forward_train": (C.c_int, [_p, _p, _p, _p, _p, _i32, _i32, _i32, _p, _p, _p, _p, _p, _p, _p]),
-    "sstg_backward": (C.c_int, [_p, _p, _p, _p, _p, _i32, _i32, _i32, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
-}
+_f32, _f64 = C.c_float, C.c_double
+_SIGS.update({
+    "sstg_train_partial_rows": (C.c_int, [_i32, _i32, _p, _p]),
+    "sstg_forward_train": (C.c_int, [_p, _p, _p, _p, _p, _i32, _i32, _i32, _i32, _p, _p, _p, _p, _p]),
+    "sstg_bn_running_update": (C.c_int, [_p, _p, _i32, _f64, _p, _p]),
+    "sstg_nll_backward": (C.c_int, [_p, _p, _p, _i32, _p, _p, _p, _p]),
+    "sstg_backward": (C.c_int, [_p, _p, _p, _p, _p, _i32, _i32, _i32, _i32, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "sstg_rel_to_abs": (C.c_int, [_p, _p, _p, _i32, _i32, _i32, _p, _p]),
+    "sstg_traj_error": (C.c_int, [_p, _p, _p, _i32, _i32, _i32, _p, _p, _p]),
+    "sstg_sgd_step": (C.c_int, [_p, _p, _i32, _f32, _f32, _p, _p]),
+})
 
 _lock = threading.Lock()
 _lib = None
@@ -57,10 +64,6 @@ def load():
         for name, (res, args) in _SIGS.items():
             fn = getattr(lib, name)
             fn.restype, fn.argtypes = res, args
-        for name, (res, args) in _OPTIONAL_SIGS.items():
-            if hasattr(lib, name):
-                fn = getattr(lib, name)
-                fn.restype, fn.argtypes = res, args
         _lib = lib
     return _lib
 

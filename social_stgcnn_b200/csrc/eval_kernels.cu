@@ -253,3 +253,72 @@ int launch_sample_ade_fde(const float* Vpred, const float* Vtr, const float* las
 }
 
 }  // namespace sstg
+
+// ---- stand-alone trajectory helpers behind the reference's metrics.py API ---------------
+namespace sstg {
+namespace {
+
+// nodes_rel_to_nodes_abs (metrics.py:69-75): abs[s,p] = fp32( fp64(sequential fp32 prefix sum) + init[p] )
+// with init in fp64 (the reference's init node is a float64 numpy array).  One thread per pedestrian.
+__global__ void rel_to_abs_kernel(const float* __restrict__ rel, const double* __restrict__ init,
+                                  const int32_t* __restrict__ seg_off, int S, int T, float* __restrict__ out) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  const int P = seg_off[S];
+  if (p >= P) return;
+  const int s = find_scene(seg_off, S, p);
+  const int n0 = seg_off[s], N = seg_off[s + 1] - n0, nl = p - n0;
+  const float2* r = reinterpret_cast<const float2*>(rel) + static_cast<size_t>(n0) * T + nl;
+  float2* o = reinterpret_cast<float2*>(out) + static_cast<size_t>(n0) * T + nl;
+  const double ix = init[2 * static_cast<size_t>(p)], iy = init[2 * static_cast<size_t>(p) + 1];
+  float cx = 0.f, cy = 0.f;
+  for (int t = 0; t < T; ++t) {
+    const float2 v = r[static_cast<size_t>(t) * N];
+    cx = __fadd_rn(cx, v.x);
+    cy = __fadd_rn(cy, v.y);
+    o[static_cast<size_t>(t) * N] = make_float2(static_cast<float>(static_cast<double>(cx) + ix),
+                                                static_cast<float>(static_cast<double>(cy) + iy));
+  }
+}
+
+// metrics.ade / metrics.fde (metrics.py:21-53) per pedestrian: sum over t of the fp64 sqrt of the
+// fp32 squared distance (sequential), and the distance at the last step.
+__global__ void traj_error_kernel(const float* __restrict__ pred, const float* __restrict__ tgt,
+                                  const int32_t* __restrict__ seg_off, int S, int T,
+                                  double* __restrict__ sum_dist, double* __restrict__ final_dist) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  const int P = seg_off[S];
+  if (p >= P) return;
+  const int s = find_scene(seg_off, S, p);
+  const int n0 = seg_off[s], N = seg_off[s + 1] - n0, nl = p - n0;
+  const float2* a = reinterpret_cast<const float2*>(pred) + static_cast<size_t>(n0) * T + nl;
+  const float2* b = reinterpret_cast<const float2*>(tgt) + static_cast<size_t>(n0) * T + nl;
+  double acc = 0.0, d = 0.0;
+  for (int t = 0; t < T; ++t) {
+    const float2 u = a[static_cast<size_t>(t) * N], v = b[static_cast<size_t>(t) * N];
+    const float dx = __fsub_rn(u.x, v.x), dy = __fsub_rn(u.y, v.y);
+    d = sqrt(static_cast<double>(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy))));
+    acc += d;
+  }
+  sum_dist[p] = acc;
+  final_dist[p] = d;
+}
+
+}  // namespace
+
+int launch_rel_to_abs(const float* rel, const double* init, const int32_t* seg_off, int S, int P, int T, float* out,
+                      cudaStream_t st) {
+  if (S == 0 || P == 0) return SSTG_OK;
+  rel_to_abs_kernel<<<(P + 127) / 128, 128, 0, st>>>(rel, init, seg_off, S, T, out);
+  SSTG_CUDA_TRY(cudaGetLastError(), "rel_to_abs launch");
+  return SSTG_OK;
+}
+
+int launch_traj_error(const float* pred, const float* tgt, const int32_t* seg_off, int S, int P, int T,
+                      double* sum_dist, double* final_dist, cudaStream_t st) {
+  if (S == 0 || P == 0) return SSTG_OK;
+  traj_error_kernel<<<(P + 127) / 128, 128, 0, st>>>(pred, tgt, seg_off, S, T, sum_dist, final_dist);
+  SSTG_CUDA_TRY(cudaGetLastError(), "traj_error launch");
+  return SSTG_OK;
+}
+
+}  // namespace sstg

@@ -104,7 +104,7 @@ int sstg_txpcnn_forward(const float* H, const int32_t* seg_off, const int32_t* t
   if (max_n > SSTG_MAX_PEDS) return SSTG_ETOOBIG;
   if (n_tiles == 0) return SSTG_OK;
   if (!H || !seg_off || !tile_off || !params || !out) return SSTG_EINVAL;
-  return launch_txpcnn_forward(H, seg_off, tile_off, n_tiles, max_n, params, out,
+  return launch_txpcnn_forward(H, seg_off, tile_off, n_tiles, max_n, params, out, nullptr, nullptr, 0,
                                static_cast<cudaStream_t>(stream));
 }
 
@@ -124,6 +124,104 @@ int sstg_sample_ade_fde(const float* Vpred, const float* Vtr, const float* last_
   if (!Vpred || !Vtr || !last_obs || !seg_off || !min_ade || !min_fde) return SSTG_EINVAL;
   return launch_sample_ade_fde(Vpred, Vtr, last_obs, seg_off, S, total_peds, K, eps, seed, eps_out, min_ade,
                                min_fde, pred_abs, flags, static_cast<cudaStream_t>(stream));
+}
+
+int sstg_rel_to_abs(const float* rel, const double* init, const int32_t* seg_off, int32_t S, int32_t total_peds,
+                    int32_t T, float* out, void* stream) {
+  if (S < 0 || total_peds < 0 || T < 1) return SSTG_EINVAL;
+  if (S == 0 || total_peds == 0) return SSTG_OK;
+  if (!rel || !init || !seg_off || !out) return SSTG_EINVAL;
+  return launch_rel_to_abs(rel, init, seg_off, S, total_peds, T, out, static_cast<cudaStream_t>(stream));
+}
+
+int sstg_traj_error(const float* pred, const float* tgt, const int32_t* seg_off, int32_t S, int32_t total_peds,
+                    int32_t T, double* sum_dist, double* final_dist, void* stream) {
+  if (S < 0 || total_peds < 0 || T < 1) return SSTG_EINVAL;
+  if (S == 0 || total_peds == 0) return SSTG_OK;
+  if (!pred || !tgt || !seg_off || !sum_dist || !final_dist) return SSTG_EINVAL;
+  return launch_traj_error(pred, tgt, seg_off, S, total_peds, T, sum_dist, final_dist,
+                           static_cast<cudaStream_t>(stream));
+}
+
+// ---- training path ------------------------------------------------------------------
+int sstg_train_partial_rows(int32_t S, int32_t n_tiles, int32_t* rows_st, int32_t* rows_tx) {
+  if (S < 0 || n_tiles < 0 || !rows_st || !rows_tx) return SSTG_EINVAL;
+  *rows_st = stgcn_train_bwd_rows(S);
+  *rows_tx = txpcnn_bwd_rows(n_tiles);
+  return SSTG_OK;
+}
+
+int sstg_forward_train(const float* V, const float* A, const int32_t* seg_off, const int64_t* a_off,
+                       const int32_t* tile_off, int32_t S, int32_t n_tiles, int32_t max_n, int32_t total_peds,
+                       const float* params, float* save, float* scene_stats, float* Vpred, void* stream) {
+  if (S < 0 || n_tiles < 0 || max_n < 1 || total_peds < 0) return SSTG_EINVAL;
+  if (max_n > SSTG_MAX_PEDS) return SSTG_ETOOBIG;
+  if (S == 0) return SSTG_OK;
+  if (!V || !A || !seg_off || !a_off || !tile_off || !params || !save || !scene_stats || !Vpred) return SSTG_EINVAL;
+  if (!aligned16(V)) return SSTG_EINVAL;
+  const long long P = total_peds;
+  float* Y = save;
+  float* Z = save + P * 40;
+  float* H = save + P * 80;
+  float* U = save + P * 120;
+  float* X = save + P * 360;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int rc = launch_stgcn_train_forward(V, A, seg_off, a_off, S, max_n, params, Y, Z, H, scene_stats, st);
+  if (rc != SSTG_OK) return rc;
+  return launch_txpcnn_forward(H, seg_off, tile_off, n_tiles, max_n, params, Vpred, U, X, P * 60, st);
+}
+
+int sstg_bn_running_update(const float* scene_stats, const int32_t* seg_off, int32_t S, double momentum,
+                           float* bn, void* stream) {
+  if (S < 0 || !(momentum >= 0.0 && momentum <= 1.0)) return SSTG_EINVAL;
+  if (S == 0) return SSTG_OK;
+  if (!scene_stats || !seg_off || !bn) return SSTG_EINVAL;
+  return launch_bn_running_update(scene_stats, seg_off, S, momentum, bn, static_cast<cudaStream_t>(stream));
+}
+
+int sstg_nll_backward(const float* Vpred, const float* Vtr, const int32_t* seg_off, int32_t S,
+                      const float* scene_weight, float* loss, float* dVpred, void* stream) {
+  if (S < 0) return SSTG_EINVAL;
+  if (S == 0) return SSTG_OK;
+  if (!Vpred || !Vtr || !seg_off || !loss || !dVpred) return SSTG_EINVAL;
+  return launch_nll_fwd_bwd(Vpred, Vtr, seg_off, S, scene_weight, loss, dVpred, static_cast<cudaStream_t>(stream));
+}
+
+int sstg_backward(const float* V, const float* A, const int32_t* seg_off, const int64_t* a_off,
+                  const int32_t* tile_off, int32_t S, int32_t n_tiles, int32_t max_n, int32_t total_peds,
+                  const float* params, const float* save, const float* scene_stats, const float* dVpred,
+                  float* dH_ws, float* partial_st, float* partial_tx, float* grad, void* stream) {
+  if (S < 0 || n_tiles < 0 || max_n < 1 || total_peds < 0) return SSTG_EINVAL;
+  if (max_n > SSTG_MAX_PEDS) return SSTG_ETOOBIG;
+  if (!grad) return SSTG_EINVAL;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (S == 0) {
+    SSTG_CUDA_TRY(cudaMemsetAsync(grad, 0, sizeof(float) * SSTG_N_PARAMS, st), "grad memset");
+    return SSTG_OK;
+  }
+  if (!V || !A || !seg_off || !a_off || !tile_off || !params || !save || !scene_stats || !dVpred || !dH_ws ||
+      !partial_st || !partial_tx)
+    return SSTG_EINVAL;
+  const long long P = total_peds;
+  const float* Y = save;
+  const float* Z = save + P * 40;
+  const float* H = save + P * 80;
+  const float* U = save + P * 120;
+  const float* X = save + P * 360;
+  int rc = launch_txpcnn_backward(dVpred, U, X, P * 60, H, seg_off, tile_off, n_tiles, max_n, params, dH_ws,
+                                  partial_tx, st);
+  if (rc != SSTG_OK) return rc;
+  rc = launch_stgcn_train_backward(V, A, seg_off, a_off, S, max_n, params, Y, Z, scene_stats, dH_ws, partial_st, st);
+  if (rc != SSTG_OK) return rc;
+  return launch_grad_finalize(partial_st, stgcn_train_bwd_rows(S), partial_tx, txpcnn_bwd_rows(n_tiles),
+                              SSTG_TXP_GRAD_STRIDE, grad, st);
+}
+
+int sstg_sgd_step(float* params, const float* grad, int32_t n, float lr, float clip_norm, float* grad_norm_out,
+                  void* stream) {
+  if (n < 0 || !params || !grad) return SSTG_EINVAL;
+  if (n == 0) return SSTG_OK;
+  return launch_sgd_step(params, grad, n, lr, clip_norm, grad_norm_out, static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

@@ -105,7 +105,32 @@ int launch_stgcn_forward(const float* V, const float* A, const int32_t* seg_off,
                          int max_n, const float* params, const float* bn, float* H, int sm_count,
                          cudaStream_t st);
 int launch_txpcnn_forward(const float* H, const int32_t* seg_off, const int32_t* tile_off, int n_tiles, int max_n,
-                          const float* params, float* out, cudaStream_t st);
+                          const float* params, float* out, float* Usave, float* Xsave, long long layer_stride,
+                          cudaStream_t st);
+int launch_rel_to_abs(const float* rel, const double* init, const int32_t* seg_off, int S, int P, int T, float* out,
+                      cudaStream_t st);
+int launch_traj_error(const float* pred, const float* tgt, const int32_t* seg_off, int S, int P, int T,
+                      double* sum_dist, double* final_dist, cudaStream_t st);
+int txpcnn_tile_width(int max_n);
+int txpcnn_bwd_rows(int n_tiles);
+int launch_txpcnn_backward(const float* dOut, const float* Usave, const float* Xsave, long long layer_stride,
+                           const float* H, const int32_t* seg_off, const int32_t* tile_off, int n_tiles, int max_n,
+                           const float* params, float* dH, float* partial, cudaStream_t st);
+int stgcn_train_bwd_rows(int S);
+int launch_stgcn_train_forward(const float* V, const float* A, const int32_t* seg_off, const int64_t* a_off, int S,
+                               int max_n, const float* params, float* Y, float* Z, float* H, float* stats,
+                               cudaStream_t st);
+int launch_stgcn_train_backward(const float* V, const float* A, const int32_t* seg_off, const int64_t* a_off, int S,
+                                int max_n, const float* params, const float* Y, const float* Z,
+                                const float* stats, const float* dH, float* partial, cudaStream_t st);
+int launch_nll_fwd_bwd(const float* Vpred, const float* Vtr, const int32_t* seg_off, int S, const float* weight,
+                       float* loss, float* dV, cudaStream_t st);
+int launch_bn_running_update(const float* stats, const int32_t* seg_off, int S, double momentum, float* bn,
+                             cudaStream_t st);
+int launch_grad_finalize(const float* part_st, int rows_st, const float* part_tx, int rows_tx, int tx_stride,
+                         float* grad, cudaStream_t st);
+int launch_sgd_step(float* params, const float* grad, int n, float lr, float clip_norm, float* grad_norm_out,
+                    cudaStream_t st);
 int launch_nll_forward(const float* Vpred, const float* Vtr, const int32_t* seg_off, int S, float* loss,
                        cudaStream_t st);
 int launch_sample_ade_fde(const float* Vpred, const float* Vtr, const float* last_obs, const int32_t* seg_off,

@@ -1,0 +1,308 @@
+// Training-path kernels, part 2: backward pass of the TXP-CNN (reference model.py:187-195,
+// differentiated by autograd in train.py:67).
+//
+// Forward (saved by txpcnn_fwd_kernel<.., SAVE=true>):
+//   x0 = view(H);  u0 = conv0(x0), x1 = PReLU0(u0);  u_k = conv_k(x_k), x_{k+1} = PReLU_k(u_k) + x_k (k=1..3);
+//   out = conv_out(x4)
+// Backward, per tile of whole scenes (the same tiling as the forward):
+//   G4 = conv_out^T(dOut);   for k = 3..1:  du_k = G_{k+1} * PReLU_k'(u_k),  G_k = G_{k+1} + conv_k^T(du_k)
+//   du_0 = G_1 * PReLU_0'(u_0),  dH = conv_0^T(du_0)
+//   dW_k = du_k (*) x_k (valid correlation over the scene's zero-padded plane), db_k = sum du_k,
+//   dslope_k = sum G_{k+1} * u_k over u_k <= 0.
+// The transposed convolutions reuse the forward's register-tiled column convolution with
+// transposed + flipped weights; a thread keeps G for its own (channel half, column) in
+// registers.  Weight gradients: a warp owns (output-channel half, input channel) units,
+// lanes stride over the tile's columns with 6x9 register accumulators, one warp reduction
+// per unit, and the totals go to a per-CTA shared accumulator that only that warp touches
+// -- so the order of every floating-point addition is fixed (no atomics).  Each CTA writes
+// its accumulator as one row of `partial`; sstg_grad_finalize adds the rows in order.
+#include "txpcnn_common.cuh"
+
+namespace sstg {
+
+namespace {
+
+using namespace txp;
+
+constexpr int B_WT = 5 * X_WL;                     // transposed weights, 12 "input" channels per layer
+constexpr int B_GRAD = SSTG_N_PARAMS - P_TP0_W;    // 7421 TXP-CNN parameters
+constexpr int B_GRAD_STRIDE = SSTG_TXP_GRAD_STRIDE;
+
+struct BSmem {
+  float wT[B_WT];
+  float slope[4];
+  int scol[2 * X_COLS];
+  int nstr[2 * X_COLS];
+  int sbase[2 * X_COLS];
+  float red[8][4];
+};
+
+__device__ __forceinline__ int w_base(int l) {
+  return l == 0 ? P_TP0_W : (l == 4 ? P_TPOUT_W : P_TP1_W + (l - 1) * P_TP_STRIDE);
+}
+__device__ __forceinline__ int b_base(int l) {
+  return l == 0 ? P_TP0_B : (l == 4 ? P_TPOUT_B : P_TP1_W + (l - 1) * P_TP_STRIDE + 1296);
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// dW[hf*6 + co][ci][kh][kw] += sum_{h, c} du[hf*6+co][h][c] * x[ci][h+kh-1][c+kw-1] over the tile's columns
+__device__ __forceinline__ void dw_unit(const float* __restrict__ DU, const float* __restrict__ XT, int Wp,
+                                        int c_end, int ci, int hf, int cin, int lane, float* __restrict__ gw) {
+  float acc[6][9];
+#pragma unroll
+  for (int co = 0; co < 6; ++co)
+#pragma unroll
+    for (int k = 0; k < 9; ++k) acc[co][k] = 0.f;
+  for (int c = 1 + lane; c <= c_end; c += 32) {
+    float x[5][3];
+    const float* xp = XT + (ci * 5) * Wp + c - 1;
+#pragma unroll
+    for (int h = 0; h < 5; ++h) {
+      x[h][0] = xp[h * Wp];
+      x[h][1] = xp[h * Wp + 1];
+      x[h][2] = xp[h * Wp + 2];
+    }
+#pragma unroll
+    for (int co = 0; co < 6; ++co) {
+      float d[5];
+#pragma unroll
+      for (int h = 0; h < 5; ++h) d[h] = DU[((hf * 6 + co) * 5 + h) * Wp + c];
+#pragma unroll
+      for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw)
+#pragma unroll
+          for (int h = 0; h < 5; ++h) {
+            const int hi = h + kh - 1;
+            if (hi >= 0 && hi < 5) acc[co][kh * 3 + kw] = fmaf(d[h], x[hi][kw], acc[co][kh * 3 + kw]);
+          }
+    }
+  }
+#pragma unroll
+  for (int co = 0; co < 6; ++co)
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+      const float s = warp_sum(acc[co][k]);
+      if (lane == 0) gw[((hf * 6 + co) * cin + ci) * 9 + k] += s;
+    }
+}
+
+template <int JX>
+__global__ void __launch_bounds__(X_THREADS, 1)
+txpcnn_bwd_kernel(const float* __restrict__ dOut, const float* __restrict__ Usave, const float* __restrict__ Xsave,
+                  long long layer_stride, const float* __restrict__ Hin, const int32_t* __restrict__ seg_off,
+                  const int32_t* __restrict__ tile_off, int n_tiles, int Wp, const float* __restrict__ params,
+                  float* __restrict__ dH, float* __restrict__ partial) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  BSmem& sm = *reinterpret_cast<BSmem*>(smem_raw);
+  float* DU = reinterpret_cast<float*>(smem_raw + ((sizeof(BSmem) + 15) & ~size_t(15)));  // [60][Wp]
+  float* XT = DU + X_ROWS * Wp;                                                          // [60][Wp]
+  float* gacc = XT + X_ROWS * Wp;                                                        // [B_GRAD_STRIDE]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int half = tid / X_COLS;
+  const int qt = tid - half * X_COLS;
+
+  // ---- transposed + flipped weights: wT[l][(b*2 + hf)*56 + a6*9 + tap'] = W_l[b][hf*6 + a6][8 - tap']
+  for (int i = tid; i < B_WT; i += X_THREADS) {
+    const int l = i / X_WL, r = i % X_WL;
+    const int b = r / (2 * X_WSLOT), r2 = r % (2 * X_WSLOT);
+    const int hf = r2 / X_WSLOT, r3 = r2 % X_WSLOT;
+    float v = 0.f;
+    if (r3 < 54) {
+      const int a = hf * 6 + r3 / 9, tap = r3 % 9;
+      const int cin = (l == 0) ? 8 : 12;
+      if (a < cin) v = params[w_base(l) + (b * cin + a) * 9 + (8 - tap)];
+    }
+    sm.wT[i] = v;
+  }
+  if (tid < 4) sm.slope[tid] = params[P_PRELUS + tid];
+  for (int i = tid; i < B_GRAD_STRIDE; i += X_THREADS) gacc[i] = 0.f;
+  float dsl[4] = {0.f, 0.f, 0.f, 0.f};
+
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int s_lo = tile_off[tile], s_hi = tile_off[tile + 1];
+    const int p_lo = seg_off[s_lo];
+    const int cols = seg_off[s_hi] - p_lo;
+    const int nsc = s_hi - s_lo;
+    const int c_end = cols + nsc - 1;  // last data column of the shared tile
+    __syncthreads();
+    for (int q = tid; q < cols; q += X_THREADS) {
+      int j = 0;
+      while (seg_off[s_lo + j + 1] - p_lo <= q) ++j;
+      const int sb = seg_off[s_lo + j] - p_lo;
+      sm.scol[q] = q + j + 1;
+      sm.nstr[q] = seg_off[s_lo + j + 1] - p_lo - sb;
+      sm.sbase[q] = sb;
+    }
+    for (int i = tid; i < (nsc + 1) * X_ROWS; i += X_THREADS) {
+      const int j = i / X_ROWS, row = i - j * X_ROWS;
+      const int col = (j < nsc) ? (seg_off[s_lo + j] - p_lo + j) : (cols + nsc);
+      DU[row * Wp + col] = 0.f;
+      XT[row * Wp + col] = 0.f;
+    }
+    __syncthreads();
+
+    int sc[JX], gN[JX];
+    long long gO[JX];
+    bool on[JX];
+    float G[JX][6][5];
+#pragma unroll
+    for (int u = 0; u < JX; ++u) {
+      const int q = qt + u * X_COLS;
+      on[u] = q < cols;
+      sc[u] = on[u] ? sm.scol[q] : 1;
+      gN[u] = on[u] ? sm.nstr[q] : 1;
+      const int sb = on[u] ? sm.sbase[q] : 0;
+      gO[u] = static_cast<long long>(p_lo + sb) * 60 + (q - sb);
+      // layer 4 (tpcnn_ouput, no activation): du_4 = dOut
+#pragma unroll
+      for (int co = 0; co < 6; ++co)
+#pragma unroll
+        for (int h = 0; h < 5; ++h) {
+          const int row = (half * 6 + co) * 5 + h;
+          const float g = on[u] ? dOut[gO[u] + static_cast<long long>(row) * gN[u]] : 0.f;
+          G[u][co][h] = g;
+          if (on[u]) DU[row * Wp + sc[u]] = g;
+        }
+    }
+    // x4 -> XT
+    {
+      const float* xb = Xsave + 3 * layer_stride + static_cast<long long>(p_lo) * 60;
+      for (int i = tid; i < X_ROWS * cols; i += X_THREADS) {
+        const int row = i / cols, q = i - row * cols;
+        const int sb = sm.sbase[q];
+        XT[row * Wp + sm.scol[q]] = xb[sb * 60 + (q - sb) + row * sm.nstr[q]];
+      }
+    }
+    __syncthreads();
+
+#pragma unroll 1
+    for (int l = 4; l >= 0; --l) {
+      const int cin = (l == 0) ? 8 : 12;
+      // ---- weight and bias gradients of layer l
+      float* gw = gacc + (w_base(l) - P_TP0_W);
+      for (int unit = warp; unit < 2 * cin; unit += 8) dw_unit(DU, XT, Wp, c_end, unit >> 1, unit & 1, cin, lane, gw);
+      for (int co = warp; co < 12; co += 8) {
+        float sb_ = 0.f;
+        for (int c = 1 + lane; c <= c_end; c += 32)
+#pragma unroll
+          for (int h = 0; h < 5; ++h) sb_ += DU[(co * 5 + h) * Wp + c];
+        sb_ = warp_sum(sb_);
+        if (lane == 0) gacc[b_base(l) - P_TP0_W + co] += sb_;
+      }
+      // ---- transposed convolution: T = conv_l^T(du_l)
+      float T[JX][6][5];
+#pragma unroll
+      for (int u = 0; u < JX; ++u) {
+#pragma unroll
+        for (int co = 0; co < 6; ++co)
+#pragma unroll
+          for (int h = 0; h < 5; ++h) T[u][co][h] = 0.f;
+        if (on[u]) conv_column<12>(DU, Wp, sc[u], sm.wT + l * X_WL, half, T[u]);
+      }
+      __syncthreads();  // every read of DU / XT for layer l is done
+      if (l == 0) {
+#pragma unroll
+        for (int u = 0; u < JX; ++u)
+          if (on[u]) {
+            const int q = qt + u * X_COLS;
+            const int sb = sm.sbase[q];
+            float* o = dH + static_cast<long long>(p_lo + sb) * 40 + (q - sb);
+#pragma unroll
+            for (int co = 0; co < 6; ++co)
+#pragma unroll
+              for (int h = 0; h < 5; ++h) {
+                const int row = (half * 6 + co) * 5 + h;
+                if (row < 40) o[static_cast<long long>(row) * gN[u]] = T[u][co][h];
+              }
+          }
+        break;
+      }
+      const int k = l - 1;  // next layer down: x_{k+1} = PReLU_k(u_k) (+ x_k for k >= 1)
+      const float slope = sm.slope[k];
+#pragma unroll
+      for (int u = 0; u < JX; ++u)
+#pragma unroll
+        for (int co = 0; co < 6; ++co)
+#pragma unroll
+          for (int h = 0; h < 5; ++h) {
+            const float g = (l == 4) ? T[u][co][h] : G[u][co][h] + T[u][co][h];
+            G[u][co][h] = g;
+            if (on[u]) {
+              const int row = (half * 6 + co) * 5 + h;
+              const float uv = Usave[k * layer_stride + gO[u] + static_cast<long long>(row) * gN[u]];
+              const bool pos = uv > 0.f;
+              if (!pos) dsl[k] = fmaf(g, uv, dsl[k]);
+              DU[row * Wp + sc[u]] = pos ? g : slope * g;
+            }
+          }
+      if (k >= 1) {
+        const float* xb = Xsave + (k - 1) * layer_stride + static_cast<long long>(p_lo) * 60;
+        for (int i = tid; i < X_ROWS * cols; i += X_THREADS) {
+          const int row = i / cols, q = i - row * cols;
+          const int sb = sm.sbase[q];
+          XT[row * Wp + sm.scol[q]] = xb[sb * 60 + (q - sb) + row * sm.nstr[q]];
+        }
+      } else {
+        const float* xb = Hin + static_cast<long long>(p_lo) * 40;
+        for (int i = tid; i < 40 * cols; i += X_THREADS) {
+          const int row = i / cols, q = i - row * cols;
+          const int sb = sm.sbase[q];
+          XT[row * Wp + sm.scol[q]] = xb[sb * 40 + (q - sb) + row * sm.nstr[q]];
+        }
+      }
+      __syncthreads();
+    }
+  }
+
+  // ---- PReLU slope gradients: CTA reduction in warp order, then the partial row
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float s = warp_sum(dsl[k]);
+    if (lane == 0) sm.red[warp][k] = s;
+  }
+  __syncthreads();
+  if (tid < 4) {
+    float s = 0.f;
+    for (int w = 0; w < 8; ++w) s += sm.red[w][tid];
+    gacc[P_PRELUS - P_TP0_W + tid] = s;
+  }
+  __syncthreads();
+  float* out = partial + static_cast<size_t>(blockIdx.x) * B_GRAD_STRIDE;
+  for (int i = tid; i < B_GRAD_STRIDE; i += X_THREADS) out[i] = gacc[i];
+}
+
+}  // namespace
+
+int txpcnn_bwd_rows(int n_tiles) {
+  int dev = 0, sms = 148;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  return n_tiles < sms ? n_tiles : sms;
+}
+
+int launch_txpcnn_backward(const float* dOut, const float* Usave, const float* Xsave, long long layer_stride,
+                           const float* H, const int32_t* seg_off, const int32_t* tile_off, int n_tiles, int max_n,
+                           const float* params, float* dH, float* partial, cudaStream_t st) {
+  if (n_tiles == 0) return SSTG_OK;
+  const int Wp = txpcnn_tile_width(max_n);
+  const size_t smem = ((sizeof(BSmem) + 15) & ~size_t(15)) + sizeof(float) * (2 * X_ROWS * Wp + B_GRAD_STRIDE);
+  const int grid = txpcnn_bwd_rows(n_tiles);
+  auto launch = [&](auto kern) -> int {
+    SSTG_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)),
+                  "txpcnn_bwd smem attr");
+    kern<<<grid, X_THREADS, smem, st>>>(dOut, Usave, Xsave, layer_stride, H, seg_off, tile_off, n_tiles, Wp, params,
+                                        dH, partial);
+    SSTG_CUDA_TRY(cudaGetLastError(), "txpcnn_bwd launch");
+    return SSTG_OK;
+  };
+  if (max_n > X_COLS) return launch(txpcnn_bwd_kernel<2>);
+  return launch(txpcnn_bwd_kernel<1>);
+}
+
+}  // namespace sstg

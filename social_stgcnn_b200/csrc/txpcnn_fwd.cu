@@ -23,74 +23,23 @@
 //   * the five layers run in place in ONE 60-row activation tile (two barriers per layer),
 //     which keeps the CTA at ~56 KB of shared memory and 4 CTAs (32 warps) per SM.
 //   * persistent grid: weights are re-laid out into shared memory once per CTA.
-#include "sstg_common.cuh"
+#include "txpcnn_common.cuh"
 
 namespace sstg {
 
 namespace {
 
-constexpr int X_COLS = SSTG_XTILE_COLS;
-constexpr int X_THREADS = 2 * X_COLS;
-constexpr int X_ROWS = T_PRED * C;  // 60 rows of the activation tile (row = channel*5 + h)
-constexpr int X_WSLOT = 56;         // 6 output channels x 9 taps, padded to a float4 multiple
-constexpr int X_W0 = 8 * 2 * X_WSLOT;
-constexpr int X_WL = 12 * 2 * X_WSLOT;
-constexpr int X_WTOTAL = X_W0 + 4 * X_WL;  // 6272 floats
+using namespace txp;
 
-struct XSmem {
-  float w[X_WTOTAL];
-  float bias[5][12];
-  float slope[4];
-  int scol[2 * X_COLS];  // tile column -> shared-memory column
-  int goff[2 * X_COLS];  // tile column -> float offset of (row 0, column) relative to the tile's first scene
-  int nstr[2 * X_COLS];  // tile column -> N of its scene (row stride in global memory)
-};
-
-// one 3x3 layer for one column: acc[6][5] += W[half] * patch
-template <int CI>
-__device__ __forceinline__ void conv_column(const float* __restrict__ act, int Wp, int sc,
-                                            const float* __restrict__ wl, int half, float (&acc)[6][5]) {
-#pragma unroll 2
-  for (int ci = 0; ci < CI; ++ci) {
-    float x[5][3];
-    const float* a = act + (ci * 5) * Wp + sc - 1;
-#pragma unroll
-    for (int h = 0; h < 5; ++h) {
-      x[h][0] = a[h * Wp + 0];
-      x[h][1] = a[h * Wp + 1];
-      x[h][2] = a[h * Wp + 2];
-    }
-    const float4* w4 = reinterpret_cast<const float4*>(wl + (ci * 2 + half) * X_WSLOT);
-    float w[X_WSLOT];
-#pragma unroll
-    for (int i = 0; i < X_WSLOT / 4; ++i) {
-      const float4 v = w4[i];
-      w[4 * i + 0] = v.x;
-      w[4 * i + 1] = v.y;
-      w[4 * i + 2] = v.z;
-      w[4 * i + 3] = v.w;
-    }
-#pragma unroll
-    for (int co = 0; co < 6; ++co)
-#pragma unroll
-      for (int kh = 0; kh < 3; ++kh)
-#pragma unroll
-        for (int kw = 0; kw < 3; ++kw) {
-          const float wv = w[co * 9 + kh * 3 + kw];
-#pragma unroll
-          for (int h = 0; h < 5; ++h) {
-            const int hi = h + kh - 1;
-            if (hi >= 0 && hi < 5) acc[co][h] = fmaf(wv, x[hi][kw], acc[co][h]);
-          }
-        }
-  }
-}
-
-template <int JX>
+// SAVE (training): also store every layer's pre-activation u_l = conv_l(x_l) and its output
+// x_{l+1} (l = 0..3) for the backward pass, in the same (12,5,N)-rows-per-scene layout as
+// `out`, layer l at float offset l * layer_stride.
+template <int JX, bool SAVE>
 __global__ void __launch_bounds__(X_THREADS)
 txpcnn_fwd_kernel(const float* __restrict__ Hin, const int32_t* __restrict__ seg_off,
                   const int32_t* __restrict__ tile_off, int n_tiles, int Wp, const float* __restrict__ params,
-                  float* __restrict__ out) {
+                  float* __restrict__ out, float* __restrict__ Usave, float* __restrict__ Xsave,
+                  long long layer_stride) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   XSmem& sm = *reinterpret_cast<XSmem*>(smem_raw);
   float* act = reinterpret_cast<float*>(smem_raw + ((sizeof(XSmem) + 15) & ~size_t(15)));  // [60][Wp]
@@ -155,13 +104,18 @@ txpcnn_fwd_kernel(const float* __restrict__ Hin, const int32_t* __restrict__ seg
     }
     __syncthreads();
 
-    int sc[JX];
+    int sc[JX], gN[JX];
+    long long gO[JX];  // float offset of (row 0, this column) in a 60-rows-per-scene buffer
     bool on[JX];
 #pragma unroll
     for (int u = 0; u < JX; ++u) {
       const int q = qt + u * X_COLS;
       on[u] = q < cols;
       sc[u] = on[u] ? sm.scol[q] : 1;
+      gN[u] = on[u] ? sm.nstr[q] : 1;
+      const int j = on[u] ? sm.scol[q] - 1 - q : 0;          // scene ordinal within the tile
+      const int sb = seg_off[s_lo + j] - p_lo;               // first column of that scene
+      gO[u] = static_cast<long long>(p_lo + sb) * 60 + (q - sb);
     }
 
 #pragma unroll 1
@@ -193,6 +147,11 @@ txpcnn_fwd_kernel(const float* __restrict__ Hin, const int32_t* __restrict__ seg
             for (int h = 0; h < 5; ++h) {
               float v = prelu(acc[u][co][h], sl);
               if (l > 0) v += act[((half * 6 + co) * 5 + h) * Wp + sc[u]];  // residual (model.py:192)
+              if (SAVE && on[u]) {
+                const long long g = l * layer_stride + gO[u] + static_cast<long long>((half * 6 + co) * 5 + h) * gN[u];
+                Usave[g] = acc[u][co][h];
+                Xsave[g] = v;
+              }
               acc[u][co][h] = v;
             }
         __syncthreads();  // everyone has read the old activations
@@ -205,19 +164,14 @@ txpcnn_fwd_kernel(const float* __restrict__ Hin, const int32_t* __restrict__ seg
               for (int h = 0; h < 5; ++h) act[((half * 6 + co) * 5 + h) * Wp + sc[u]] = acc[u][co][h];
         __syncthreads();
       } else {
-        float* Ob = out + static_cast<size_t>(p_lo) * 60;
 #pragma unroll
         for (int u = 0; u < JX; ++u)
           if (on[u]) {
-            const int q = qt + u * X_COLS;
-            const int N = sm.nstr[q];
-            const int j = sm.scol[q] - 1 - q;               // scene ordinal within the tile
-            const int sb = seg_off[s_lo + j] - p_lo;        // first column of that scene
-            float* o = Ob + static_cast<size_t>(sb) * 60 + (q - sb);
+            float* o = out + gO[u];
 #pragma unroll
             for (int co = 0; co < 6; ++co)
 #pragma unroll
-              for (int h = 0; h < 5; ++h) o[((half * 6 + co) * 5 + h) * N] = acc[u][co][h];
+              for (int h = 0; h < 5; ++h) o[((half * 6 + co) * 5 + h) * gN[u]] = acc[u][co][h];
           }
       }
     }
@@ -226,14 +180,19 @@ txpcnn_fwd_kernel(const float* __restrict__ Hin, const int32_t* __restrict__ seg
 
 }  // namespace
 
+int txpcnn_tile_width(int max_n) {
+  int Wp = txp::X_COLS + SSTG_XTILE_MAX_SCENES + 1;
+  if (max_n + 2 > Wp) Wp = max_n + 2;
+  return (Wp + 3) & ~3;
+}
+
 int launch_txpcnn_forward(const float* H, const int32_t* seg_off, const int32_t* tile_off, int n_tiles, int max_n,
-                          const float* params, float* out, cudaStream_t st) {
+                          const float* params, float* out, float* Usave, float* Xsave, long long layer_stride,
+                          cudaStream_t st) {
   if (n_tiles == 0) return SSTG_OK;
   // widest tile: up to X_COLS columns of up to MAX_SCENES scenes, or one big scene;
   // one zero separator column before every scene and one after the last
-  int Wp = X_COLS + SSTG_XTILE_MAX_SCENES + 1;
-  if (max_n + 2 > Wp) Wp = max_n + 2;
-  Wp = (Wp + 3) & ~3;
+  const int Wp = txpcnn_tile_width(max_n);
   const size_t smem = ((sizeof(XSmem) + 15) & ~size_t(15)) + sizeof(float) * X_ROWS * Wp;
   int dev = 0, sms = 148;
   SSTG_CUDA_TRY(cudaGetDevice(&dev), "cudaGetDevice");
@@ -246,12 +205,13 @@ int launch_txpcnn_forward(const float* H, const int32_t* seg_off, const int32_t*
     if (per_sm < 1) per_sm = 1;
     const long long want = static_cast<long long>(sms) * per_sm;
     const int grid = static_cast<int>(n_tiles < want ? n_tiles : want);
-    kern<<<grid, X_THREADS, smem, st>>>(H, seg_off, tile_off, n_tiles, Wp, params, out);
+    kern<<<grid, X_THREADS, smem, st>>>(H, seg_off, tile_off, n_tiles, Wp, params, out, Usave, Xsave, layer_stride);
     SSTG_CUDA_TRY(cudaGetLastError(), "txpcnn launch");
     return SSTG_OK;
   };
-  if (max_n > X_COLS) return launch(txpcnn_fwd_kernel<2>);
-  return launch(txpcnn_fwd_kernel<1>);
+  const bool save = Usave != nullptr && Xsave != nullptr;
+  if (max_n > X_COLS) return save ? launch(txpcnn_fwd_kernel<2, true>) : launch(txpcnn_fwd_kernel<2, false>);
+  return save ? launch(txpcnn_fwd_kernel<1, true>) : launch(txpcnn_fwd_kernel<1, false>);
 }
 
 }  // namespace sstg

@@ -269,3 +269,156 @@ class InferenceEngine:
     @staticmethod
     def d2h_bytes(plan: ScenePlan) -> int:
         return plan.P * 2 * 8
+
+
+# --------------------------------------------------------------------------
+# training path: functional ops
+# --------------------------------------------------------------------------
+def partial_rows(plan: ScenePlan):
+    """Rows of the two partial-gradient buffers sstg_backward needs on the current device."""
+    a, b = np.zeros(1, np.int32), np.zeros(1, np.int32)
+    L.check(L.load().sstg_train_partial_rows(plan.S, plan.n_tiles, a.ctypes.data, b.ctypes.data),
+            "sstg_train_partial_rows")
+    return int(a[0]), int(b[0])
+
+
+def forward_train(dp: DevicePlan, V, A, params, *, save=None, scene_stats=None, out=None):
+    """social_stgcnn.forward in train mode (per-scene BatchNorm batch statistics) for the packed
+    batch.  Returns (V_pred (5,12,N) blocks, save, scene_stats [S,30])."""
+    h, dev = dp.host, dp.device
+    for t, w in ((V, "V"), (A, "A"), (params, "params")):
+        _need(t, torch.float32, w, dev)
+    if h.T != L.T_OBS:
+        raise AssertionError(f"A.size(0) must equal the st_gcn kernel size {L.T_OBS}")  # model.py:65
+    if save is None:
+        save = torch.empty(h.P * L.SAVE_FLOATS_PER_PED, dtype=torch.float32, device=dev)
+    if scene_stats is None:
+        scene_stats = torch.empty(h.S, L.N_BN, dtype=torch.float32, device=dev)
+    if out is None:
+        out = torch.empty(h.P * 60, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        L.check(L.load().sstg_forward_train(_ptr(V), _ptr(A), _ptr(dp.seg_off), _ptr(dp.a_off), _ptr(dp.tile_off),
+                                            h.S, h.n_tiles, h.max_n, h.P, _ptr(params), _ptr(save),
+                                            _ptr(scene_stats), _ptr(out), _stream(dev)), "sstg_forward_train")
+    return out, save, scene_stats
+
+
+def bn_running_update(dp: DevicePlan, scene_stats, bn, momentum: float = 0.1):
+    """Apply the S per-scene BatchNorm updates to the running statistics bn[30], in scene order."""
+    h, dev = dp.host, dp.device
+    _need(scene_stats, torch.float32, "scene_stats", dev)
+    _need(bn, torch.float32, "bn", dev)
+    with torch.cuda.device(dev):
+        L.check(L.load().sstg_bn_running_update(_ptr(scene_stats), _ptr(dp.seg_off), h.S, float(momentum), _ptr(bn),
+                                                _stream(dev)), "sstg_bn_running_update")
+    return bn
+
+
+def nll_backward(dp: DevicePlan, Vpred, Vtr, scene_weight=None, *, loss=None, dVpred=None):
+    """bivariate_loss per scene and scene_weight[s] * d loss[s] / d V_pred."""
+    h, dev = dp.host, dp.device
+    _need(Vpred, torch.float32, "Vpred", dev)
+    _need(Vtr, torch.float32, "Vtr", dev)
+    if scene_weight is not None:
+        _need(scene_weight, torch.float32, "scene_weight", dev)
+        if scene_weight.numel() != h.S:
+            raise ValueError("scene_weight must hold one float per scene")
+    if loss is None:
+        loss = torch.empty(h.S, dtype=torch.float32, device=dev)
+    if dVpred is None:
+        dVpred = torch.empty(h.P * 60, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        L.check(L.load().sstg_nll_backward(_ptr(Vpred), _ptr(Vtr), _ptr(dp.seg_off), h.S, _ptr(scene_weight),
+                                           _ptr(loss), _ptr(dVpred), _stream(dev)), "sstg_nll_backward")
+    return loss, dVpred
+
+
+def backward(dp: DevicePlan, V, A, params, save, scene_stats, dVpred, *, grad=None, ws=None):
+    """loss.backward() for the packed batch: flat gradient [7563] in named_parameters() order."""
+    h, dev = dp.host, dp.device
+    for t, w in ((V, "V"), (A, "A"), (params, "params"), (save, "save"), (scene_stats, "scene_stats"),
+                 (dVpred, "dVpred")):
+        _need(t, torch.float32, w, dev)
+    if grad is None:
+        grad = torch.empty(L.N_PARAMS, dtype=torch.float32, device=dev)
+    if ws is None:
+        ws = {}
+    with torch.cuda.device(dev):
+        rs, rt = partial_rows(h)
+        f = torch.float32
+        if ws.get("dH") is None or ws["dH"].numel() < h.P * 40:
+            ws["dH"] = torch.empty(max(1, h.P * 40), dtype=f, device=dev)
+        if ws.get("pst") is None or ws["pst"].numel() < rs * L.ST_PARAMS:
+            ws["pst"] = torch.empty(max(1, rs * L.ST_PARAMS), dtype=f, device=dev)
+        if ws.get("ptx") is None or ws["ptx"].numel() < rt * L.TXP_GRAD_STRIDE:
+            ws["ptx"] = torch.empty(max(1, rt * L.TXP_GRAD_STRIDE), dtype=f, device=dev)
+        L.check(L.load().sstg_backward(_ptr(V), _ptr(A), _ptr(dp.seg_off), _ptr(dp.a_off), _ptr(dp.tile_off), h.S,
+                                       h.n_tiles, h.max_n, h.P, _ptr(params), _ptr(save), _ptr(scene_stats),
+                                       _ptr(dVpred), _ptr(ws["dH"]), _ptr(ws["pst"]), _ptr(ws["ptx"]), _ptr(grad),
+                                       _stream(dev)), "sstg_backward")
+    return grad
+
+
+def sgd_step(params, grad, lr: float, clip_norm: float = 0.0, grad_norm_out=None):
+    """optimizer.step() of train.py:197 (+ clip_grad_norm_ of train.py:69-70 when clip_norm > 0)."""
+    dev = params.device
+    _need(params, torch.float32, "params", dev)
+    _need(grad, torch.float32, "grad", dev)
+    with torch.cuda.device(dev):
+        L.check(L.load().sstg_sgd_step(_ptr(params), _ptr(grad), params.numel(), float(lr), float(clip_norm or 0.0),
+                                       _ptr(grad_norm_out), _stream(dev)), "sstg_sgd_step")
+    return params
+
+
+def group_weights(S: int, batch_size: int) -> np.ndarray:
+    """Loss weights of one optimiser group of train() (train.py:58-66): every scene but the
+    last is scored with weight 1/batch_size; the last one is forwarded (it updates the BN
+    running statistics) but contributes no loss."""
+    w = np.full(S, 1.0 / batch_size, np.float32)
+    if S > 0:
+        w[-1] = 0.0
+    return w
+
+
+class TrainEngine:
+    """Weights + BN buffers resident on one GPU; `step` runs one optimiser group of the
+    reference's train() (train.py:28-79) on a packed ragged batch:
+    graph build -> train-mode forward -> NLL + gradient -> backward -> BN running stats -> SGD."""
+
+    def __init__(self, params, bn, device="cuda", num_batches_tracked: int = 0):
+        device = torch.device(device)
+        if device.type != "cuda":
+            raise RuntimeError("TrainEngine needs a CUDA device (no CPU fallback)")
+        if device.index is None:
+            device = torch.device("cuda", torch.cuda.current_device())
+        L.load()
+        self.device = device
+        self.params = torch.as_tensor(np.asarray(params, np.float32)).reshape(-1).to(device).contiguous().clone()
+        self.bn = torch.as_tensor(np.asarray(bn, np.float32)).reshape(-1).to(device).contiguous().clone()
+        if self.params.numel() != L.N_PARAMS or self.bn.numel() != L.N_BN:
+            raise ValueError("params must hold 7563 floats and bn 30 floats")
+        self.num_batches_tracked = int(num_batches_tracked)
+        self.grad = torch.zeros(L.N_PARAMS, dtype=torch.float32, device=device)
+        self._ws: Dict[str, torch.Tensor] = {}
+
+    def forward_backward(self, plan: ScenePlan, obs_rel, pred_rel, scene_weight, *, graph_fp64: bool = True):
+        """Everything of a group except the parameter update.  Returns dict(loss[S], grad[7563],
+        scene_stats[S,30], V_pred)."""
+        dp = plan.on(self.device)
+        V, A = graph_build(dp, obs_rel, L.T_OBS, fp64=graph_fp64)
+        V_tr, _ = graph_build(dp, pred_rel, L.T_PRED, v_only=True)
+        vp, save, stats = forward_train(dp, V, A, self.params)
+        w = torch.as_tensor(np.asarray(scene_weight, np.float32)).to(self.device) \
+            if not isinstance(scene_weight, torch.Tensor) else scene_weight
+        loss, dvp = nll_backward(dp, vp, V_tr, w)
+        backward(dp, V, A, self.params, save, stats, dvp, grad=self.grad, ws=self._ws)
+        return {"loss": loss, "grad": self.grad, "scene_stats": stats, "V_pred": vp, "weight": w}
+
+    def step(self, plan: ScenePlan, obs_rel, pred_rel, batch_size: int, lr: float, clip_grad=None,
+             *, graph_fp64: bool = True):
+        """One optimiser group: returns the group loss (sum_i w_i * l_i) as a 0-dim device tensor."""
+        r = self.forward_backward(plan, obs_rel, pred_rel, group_weights(plan.S, batch_size), graph_fp64=graph_fp64)
+        bn_running_update(plan.on(self.device), r["scene_stats"], self.bn)
+        self.num_batches_tracked += plan.S
+        sgd_step(self.params, self.grad, lr, clip_grad or 0.0)
+        return (r["loss"] * r["weight"]).sum()

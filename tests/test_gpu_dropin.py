@@ -1,0 +1,171 @@
+"""GPU tests of the drop-in Python surface (social_stgcnn_b200.{model,metrics,utils}): the
+reference's own call sequences (train.py:38-74, test.py:38-123, utils.py:86-228) run against
+the CUDA-backed replacements and are compared with the golden vectors of the real reference."""
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from tests.common import GOLD, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    return torch.device("cuda", 0)
+
+
+def _state_dict(golden, ckpt):
+    from oracle import stgcnn_oracle as O
+    params, bn = golden.params(ckpt)
+    sd = dict(O.unflatten_params(params))
+    sd.update(O.unflatten_bn(bn))
+    nbt = int(golden.weights[f"{ckpt}.nbt"][0])
+    for p in ("st_gcns.0.tcn.0", "st_gcns.0.tcn.3", "st_gcns.0.residual.1"):
+        sd[p + ".num_batches_tracked"] = torch.tensor(nbt)
+    return sd
+
+
+def _model(golden, dev, ckpt="eth"):
+    from social_stgcnn_b200.model import social_stgcnn
+    m = social_stgcnn(n_stgcnn=1, n_txpcnn=5, output_feat=5, seq_len=8, kernel_size=3, pred_seq_len=12)
+    m.load_state_dict(_state_dict(golden, ckpt), strict=True)       # exactly the checkpoint's 40 keys
+    return m.to(dev)
+
+
+def _scene(golden, name, dev):
+    g = golden.graph
+    t = lambda k: torch.from_numpy(g[f"{name}.{k}"]).to(dev)
+    return t("V_obs")[None], t("A_obs")[None], t("V_tr")[None]        # the DataLoader's leading 1
+
+
+def test_eval_forward_is_the_reference(golden, dev):
+    m = _model(golden, dev).eval()
+    for name in ("eth000", "univ000", "syn64", "syn9dup"):
+        V_obs, A_obs, _ = _scene(golden, name, dev)
+        a_in = A_obs.squeeze(0)
+        with torch.no_grad():
+            vp, a_out = m(V_obs.permute(0, 3, 1, 2), a_in)            # test.py:38-40
+        assert a_out is a_in                                          # model.py:198 returns `a` itself
+        assert rel_err(vp.cpu().numpy(), golden.fwd[f"eth.{name}.eval"]) < 1e-5, name
+    with pytest.raises(AssertionError):                               # model.py:65
+        m(V_obs.permute(0, 3, 1, 2), a_in[:7])
+
+
+def test_train_loop_of_the_reference(golden, dev):
+    """train.py:38-74 verbatim on the drop-ins (bs = 4, group g0): accumulated loss, .grad of every
+    parameter, BN buffers and num_batches_tracked equal the reference's."""
+    from social_stgcnn_b200.metrics import bivariate_loss
+    Lz = golden.loss
+    names = [str(n) for n in Lz["train.g0.names"]]
+    m = _model(golden, dev).train()
+    opt = torch.optim.SGD(m.parameters(), lr=0.0)
+    batch_size, loader_len, turn_point = 4, len(names), len(names) - 1
+    batch_count, is_fst_loss, loss_batch = 0, True, 0.0
+    for cnt, name in enumerate(names):
+        batch_count += 1
+        V_obs, A_obs, V_tr = _scene(golden, name, dev)
+        opt.zero_grad()
+        V_pred, _ = m(V_obs.permute(0, 3, 1, 2), A_obs.squeeze(0))
+        V_pred = V_pred.permute(0, 2, 3, 1).squeeze(0)
+        if batch_count % batch_size != 0 and cnt != turn_point:
+            l = bivariate_loss(V_pred, V_tr.squeeze(0))
+            loss = l if is_fst_loss else loss + l
+            is_fst_loss = False
+        else:
+            loss = loss / batch_size
+            is_fst_loss = True
+            loss.backward()
+            opt.step()
+            loss_batch += loss.item()
+    assert loader_len == 4
+    ref_loss = float(Lz["train.g0.loss"][0])
+    assert abs(loss_batch - ref_loss) < 1e-5 * max(1.0, abs(ref_loss))
+    ref_grad, none_mask = Lz["train.g0.grad"], Lz["train.g0.grad_is_none"]
+    off = 0
+    scale = np.abs(ref_grad).max()
+    for k, p in m.named_parameters():
+        n = p.numel()
+        if none_mask[off]:
+            assert p.grad is None, k                                   # never executed (model.py:191)
+        else:
+            err = np.abs(p.grad.cpu().numpy().reshape(-1) - ref_grad[off:off + n]).max() / scale
+            assert err < 5e-5, (k, err)
+        off += n
+    from oracle import stgcnn_oracle as O
+    assert np.allclose(O.flatten_bn(m.state_dict()), Lz["train.g0.bn"], rtol=1e-5, atol=1e-7)
+    assert int(m.state_dict()["st_gcns.0.tcn.0.num_batches_tracked"]) == int(Lz["train.g0.nbt"][0])
+
+
+def test_bivariate_loss_value_and_autograd(golden, dev):
+    from oracle import stgcnn_oracle as O
+    from social_stgcnn_b200.metrics import bivariate_loss
+    rng = np.random.default_rng(11)
+    vp = rng.normal(0, 0.6, (12, 7, 5)).astype(np.float32)
+    vt = rng.normal(0, 0.6, (12, 7, 2)).astype(np.float32)
+    a = torch.tensor(vp, device=dev, requires_grad=True)
+    l = bivariate_loss(a, torch.tensor(vt, device=dev))
+    (3.0 * l).backward()
+    b = torch.tensor(vp, dtype=torch.float64, requires_grad=True)
+    lr = O.bivariate_loss(b, torch.tensor(vt, dtype=torch.float64))
+    (3.0 * lr).backward()
+    assert l.dim() == 0 and abs(float(l) - float(lr)) < 1e-5 * abs(float(lr))
+    assert np.abs(a.grad.cpu().numpy() - b.grad.numpy()).max() < 1e-5 * np.abs(b.grad.numpy()).max()
+
+
+def test_ade_fde_and_rel_to_abs(golden, dev):
+    from oracle import stgcnn_oracle as O
+    from social_stgcnn_b200 import metrics as M
+    rng = np.random.default_rng(2)
+    preds = [rng.normal(0, 2, (12, n, 2)).astype(np.float32) for n in (3, 1, 8)]
+    tgts = [rng.normal(0, 2, (12, n, 2)).astype(np.float32) for n in (3, 1, 8)]
+    counts = [3, 1, 6]
+
+    def ref(final_only):
+        tot = 0.0
+        for p, t, c in zip(preds, tgts, counts):
+            s = 0.0
+            for i in range(c):
+                for k in (range(11, 12) if final_only else range(12)):
+                    dx, dy = p[k, i, 0] - t[k, i, 0], p[k, i, 1] - t[k, i, 1]
+                    s += math.sqrt(np.float32(dx * dx) + np.float32(dy * dy))
+            tot += s / (c if final_only else c * 12)
+        return tot / len(preds)
+
+    assert abs(M.ade(preds, tgts, counts) - ref(False)) < 1e-12 * ref(False) + 1e-15
+    assert abs(M.fde(preds, tgts, counts) - ref(True)) < 1e-12 * ref(True) + 1e-15
+    rel = rng.normal(0, 0.3, (12, 5, 2)).astype(np.float32)
+    init = rng.normal(0, 8, (5, 2))
+    assert np.array_equal(M.nodes_rel_to_nodes_abs(rel, init), O.rel_to_abs(rel, init))
+    seq = rng.normal(0, 1, (1, 4, 2, 8)).astype(np.float32)
+    V = M.seq_to_nodes(seq)
+    assert V.shape == (8, 4, 2) and V.dtype == np.float64 and np.array_equal(V[3, 2], seq[0, 2, :, 3])
+
+
+def test_seq_to_graph_and_dataset(golden, dev):
+    """utils.seq_to_graph on CPU tensors (the reference's calling convention) and the whole
+    TrajectoryDataset on the shipped eth/test file: 70 scenes, 181 pedestrians, every A_obs /
+    A_tr bit-identical to the reference's networkx graphs."""
+    from social_stgcnn_b200.utils import TrajectoryDataset, seq_to_graph
+    g = golden.graph
+    V, A = seq_to_graph(torch.from_numpy(g["univ000.obs"]), torch.from_numpy(g["univ000.obs_rel"]), True)
+    assert not V.is_cuda and np.array_equal(A.numpy().view(np.uint32), g["univ000.A_obs"].view(np.uint32))
+    assert np.array_equal(V.numpy(), g["univ000.V_obs"])
+    d = TrajectoryDataset(os.path.join(GOLD, "datasets", "eth", "test") + "/", obs_len=8, pred_len=12, skip=1,
+                          norm_lap_matr=True)
+    assert len(d) == 70 and d.obs_traj.shape[0] == 181
+    for i in range(70):
+        item = d[i]
+        assert len(item) == 10
+        name = f"eth{i:03d}"
+        assert np.array_equal(item[2].numpy(), g[f"{name}.obs_rel"]), name
+        assert np.array_equal(item[6].numpy(), g[f"{name}.V_obs"]), name
+        assert np.array_equal(item[7].numpy().view(np.uint32), g[f"{name}.A_obs"].view(np.uint32)), name
+        assert np.array_equal(item[9].numpy().view(np.uint32), g[f"{name}.A_tr"].view(np.uint32)), name
+    with pytest.raises(ValueError):
+        TrajectoryDataset(os.path.join(GOLD, "datasets", "eth", "test") + "/", obs_len=8, pred_len=12, delim=" ")

@@ -1,0 +1,79 @@
+"""CPU tests of the host-side logic that needs no GPU: the dataset windowing against the
+reference's own scenes (golden), the drop-in module's state_dict contract, loud failure
+without CUDA, and the optimiser-group loss weights."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from tests.common import GOLD
+
+
+def test_dataset_windowing_matches_reference(golden):
+    """utils.load_scenes (vectorised) == the reference's TrajectoryDataset windowing
+    (utils.py:121-170) on the shipped eth/test file: 70 scenes, 181 pedestrians, identical
+    rel/abs trajectories in identical order."""
+    from social_stgcnn_b200.utils import load_scenes
+    seqs, rels, masks, nl, counts, max_peds = load_scenes(os.path.join(GOLD, "datasets", "eth", "test") + "/",
+                                                          8, 12, 1, 0.002, 1, "\t")
+    assert len(seqs) == 70 and sum(counts) == 181 and min(counts) == 2 and max(counts) == 5
+    g = golden.graph
+    for i in range(70):
+        name = f"eth{i:03d}"
+        assert np.array_equal(rels[i][:, :, :8].astype(np.float32), g[f"{name}.obs_rel"]), name
+        assert np.array_equal(rels[i][:, :, 8:].astype(np.float32), g[f"{name}.pred_rel"]), name
+        assert np.array_equal(seqs[i][:, :, :8].astype(np.float32), g[f"{name}.obs"]), name
+        assert masks[i].shape == (counts[i], 20) and nl[i].shape == (counts[i],)
+
+
+def test_module_state_dict_contract():
+    """Exactly the 40 keys / shapes of checkpoint/*/val_best.pth, parameters in
+    the flat block's order."""
+    from oracle import stgcnn_oracle as O
+    from social_stgcnn_b200.model import social_stgcnn
+    m = social_stgcnn(n_stgcnn=1, n_txpcnn=5, output_feat=5, seq_len=8, kernel_size=3, pred_seq_len=12)
+    named = list(m.named_parameters())
+    assert [k for k, _ in named] == [k for k, _ in O.PARAM_LAYOUT]
+    assert [tuple(p.shape) for _, p in named] == [tuple(s) for _, s in O.PARAM_LAYOUT]
+    sd = m.state_dict()
+    expect = {k for k, _ in O.PARAM_LAYOUT} | set(O.BN_LAYOUT) | {
+        p + ".num_batches_tracked" for p in ("st_gcns.0.tcn.0", "st_gcns.0.tcn.3", "st_gcns.0.residual.1")}
+    assert set(sd.keys()) == expect and len(sd) == 40
+    assert m._flat_params().numel() == 7563 and m._flat_bn().numel() == 30
+
+
+def test_default_init_matches_torch_layers_in_reference_order():
+    """Same seed -> same initial weights as building the reference's layer list in its definition
+    order (model.py:109-143,164-178): the containers are created in that order."""
+    import torch.nn as nn
+    from social_stgcnn_b200.model import social_stgcnn
+    torch.manual_seed(7)
+    m = social_stgcnn(n_stgcnn=1, n_txpcnn=5, output_feat=5, seq_len=8, kernel_size=3, pred_seq_len=12)
+    torch.manual_seed(7)
+    ref = [nn.Conv2d(2, 5, (1, 1)), nn.BatchNorm2d(5), nn.PReLU(), nn.Conv2d(5, 5, (3, 1), (1, 1), (1, 0)),
+           nn.BatchNorm2d(5), nn.Conv2d(2, 5, 1, stride=(1, 1)), nn.BatchNorm2d(5), nn.PReLU(),
+           nn.Conv2d(8, 12, 3, padding=1)] + [nn.Conv2d(12, 12, 3, padding=1) for _ in range(5)] + \
+          [nn.PReLU() for _ in range(5)]
+    flat_ref = torch.cat([p.reshape(-1) for l in ref for p in l.parameters()])
+    assert torch.equal(m._flat_params(), flat_ref)
+
+
+def test_no_cpu_fallback():
+    from social_stgcnn_b200.metrics import bivariate_loss
+    from social_stgcnn_b200.model import social_stgcnn
+    m = social_stgcnn(n_stgcnn=1, n_txpcnn=5, output_feat=5, seq_len=8, kernel_size=3, pred_seq_len=12)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m(torch.zeros(1, 2, 8, 3), torch.zeros(8, 3, 3))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        bivariate_loss(torch.zeros(12, 3, 5), torch.zeros(12, 3, 2))
+    with pytest.raises(NotImplementedError):
+        social_stgcnn(n_stgcnn=2, n_txpcnn=5)(torch.zeros(1, 2, 8, 3), torch.zeros(8, 3, 3))
+
+
+def test_group_weights():
+    from social_stgcnn_b200.engine import group_weights
+    w = group_weights(128, 128)
+    assert w.dtype == np.float32 and w[-1] == 0 and np.all(w[:-1] == np.float32(1 / 128))
+    assert list(group_weights(3, 4)) == [0.25, 0.25, 0.0]        # short trailing group keeps the divisor
+    assert group_weights(0, 4).size == 0
