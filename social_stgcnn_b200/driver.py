@@ -1,0 +1,117 @@
+"""Packed-batch replacements for the reference's two scene loops: `test()` (test.py:18-127) and
+`train()` / `vald()` (train.py:28-122).  Same inputs (a TrajectoryDataset, the weights), same
+return values, but every scene of the split goes through the kernels in one packed batch
+(evaluation) or one packed batch per optimiser group (training) instead of a batch-1
+DataLoader loop.  Host code here is orchestration only (index gathers, bookkeeping).
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional
+
+import numpy as np
+import torch
+
+from . import _lib as L
+from . import engine as E
+
+
+def _packed(dataset, dev):
+    pk = getattr(dataset, "packed", None)
+    if pk is None or torch.device(pk["device"]) != dev:
+        raise RuntimeError("dataset must be a social_stgcnn_b200.utils.TrajectoryDataset built on the engine's device")
+    return pk
+
+
+def _rel_to_abs(dp, rel_blocks, init, T):
+    out = torch.empty_like(rel_blocks)
+    dev = dp.device
+    with torch.cuda.device(dev):
+        L.check(L.load().sstg_rel_to_abs(rel_blocks.data_ptr(), init.data_ptr(), dp.seg_off.data_ptr(), dp.host.S,
+                                         dp.host.P, T, out.data_ptr(), torch.cuda.current_stream(dev).cuda_stream),
+                "sstg_rel_to_abs")
+    return out
+
+
+def evaluate(dataset, engine: E.InferenceEngine, KSTEPS: int = 20, seed: int = 0, eps: Optional[torch.Tensor] = None,
+             want_raw: bool = False, exact: bool = True):
+    """test() of the reference (test.py:18-127) over a whole split.
+
+    Returns (ade_, fde_, raw_data_dict): the means over ALL pedestrians of the per-pedestrian
+    minima over KSTEPS samples (test.py:121-126), and -- if `want_raw` -- the reference's
+    raw_data_dict {step: {'obs', 'trgt', 'pred': [KSTEPS arrays]}} of absolute trajectories
+    (test.py:87-105), step counted from 1.  `exact` keeps the reference's fp64 rounding islands
+    (graph, distances); `eps` injects the standard-normal noise (layout (K,12,N,2) per scene)."""
+    dev = engine.device
+    pk = _packed(dataset, dev)
+    plan = dataset.plan_obs
+    r = engine.infer(plan, pk["obs_rel"], pk["pred_rel"], pk["last_obs"], KSTEPS, eps=eps, seed=seed,
+                     graph_fp64=exact, fp64_dist=exact, want_pred=want_raw)
+    P = plan.P
+    ade_ = float(r["min_ade"].sum()) / P
+    fde_ = float(r["min_fde"].sum()) / P
+    raw: Dict[int, dict] = {}
+    if want_raw:
+        dp = plan.on(dev)
+        first = dataset.obs_traj[:, :, 0].to(dev).double().contiguous()
+        last = dataset.obs_traj[:, :, -1].to(dev).double().contiguous()
+        obs_abs = _rel_to_abs(dp, r["V_obs"], first, L.T_OBS).cpu().numpy()
+        tgt_abs = _rel_to_abs(dp, r["V_tr"], last, L.T_PRED).cpu().numpy()
+        pred = r["pred_abs"].cpu().numpy()
+        for s in range(plan.S):
+            o, n = int(plan.seg_off[s]), int(plan.n_peds[s])
+            pr = pred[o * KSTEPS * 24:(o + n) * KSTEPS * 24].reshape(KSTEPS, L.T_PRED, n, 2)
+            raw[s + 1] = {"obs": obs_abs[o * 16:(o + n) * 16].reshape(L.T_OBS, n, 2).copy(),
+                          "trgt": tgt_abs[o * 24:(o + n) * 24].reshape(L.T_PRED, n, 2).copy(),
+                          "pred": [pr[k].copy() for k in range(KSTEPS)]}
+    return ade_, fde_, raw
+
+
+def _group_rows(seg, scenes, dev):
+    idx = np.concatenate([np.arange(seg[s], seg[s + 1]) for s in scenes]) if len(scenes) else np.zeros(0, np.int64)
+    return torch.from_numpy(idx.astype(np.int64)).to(dev)
+
+
+def train_epoch(dataset, engine: E.TrainEngine, batch_size: int = 128, lr: float = 0.01,
+                clip_grad: Optional[float] = None, order=None, trainer=None):
+    """train() of the reference (train.py:28-79) over one epoch.
+
+    `order` is the scene order of the epoch (the DataLoader's shuffle; default: dataset order).
+    Scenes are taken in groups of `batch_size`; each group is one packed forward/backward and one
+    SGD step, with the reference's accumulation rule (the last scene of a group is forwarded but
+    not scored, divisor batch_size; train.py:58-66).  Returns loss_batch / batch_count exactly as
+    the reference does (sum of the group losses / number of scenes, train.py:76-79).
+    `trainer` (parallel.DistributedTrainer) spreads every group over the ranks."""
+    dev = engine.device
+    pk = _packed(dataset, dev)
+    S = len(dataset)
+    order = np.arange(S) if order is None else np.asarray(order)
+    n_all = np.asarray(dataset.plan_obs.n_peds)
+    seg = dataset.plan_obs.seg_off
+    loss_batch = torch.zeros((), dtype=torch.float64, device=dev)
+    for g0 in range(0, S, batch_size):
+        scenes = order[g0:g0 + batch_size]
+        # (a trailing group of ONE scene has no scored scene: zero loss, zero gradient -- the
+        #  reference crashes there on a freed autograd graph, SURVEY a-8; no shipped split hits it)
+        rows = _group_rows(seg, scenes, dev)
+        obs, pred = pk["obs_rel"].index_select(0, rows), pk["pred_rel"].index_select(0, rows)
+        if trainer is not None:
+            loss_batch += trainer.step(n_all[scenes], obs, pred, batch_size, lr, clip_grad)
+        else:
+            loss_batch += engine.step(E.ScenePlan(n_all[scenes]), obs, pred, batch_size, lr, clip_grad).double()
+    return float(loss_batch) / S
+
+
+def validate_epoch(dataset, engine: E.InferenceEngine, batch_size: int = 128):
+    """vald() of the reference (train.py:81-122): eval-mode forward, same accumulation rule,
+    no parameter update.  Returns loss_batch / batch_count."""
+    dev = engine.device
+    pk = _packed(dataset, dev)
+    plan = dataset.plan_obs
+    r = engine.infer(plan, pk["obs_rel"], pk["pred_rel"], pk["last_obs"], K=1, graph_fp64=True)
+    loss = E.nll_forward(plan.on(dev), r["V_pred"], r["V_tr"]).double().cpu().numpy()
+    S = plan.S
+    tot = 0.0
+    for g0 in range(0, S, batch_size):
+        g = loss[g0:g0 + batch_size]
+        tot += float(g[:-1].sum()) / batch_size
+    return tot / S

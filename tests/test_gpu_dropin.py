@@ -169,3 +169,67 @@ def test_seq_to_graph_and_dataset(golden, dev):
         assert np.array_equal(item[9].numpy().view(np.uint32), g[f"{name}.A_tr"].view(np.uint32)), name
     with pytest.raises(ValueError):
         TrajectoryDataset(os.path.join(GOLD, "datasets", "eth", "test") + "/", obs_len=8, pred_len=12, delim=" ")
+
+
+def test_driver_evaluate_is_test_py(golden, dev):
+    """driver.evaluate == test() of the reference on eth/test with the same injected noise:
+    dataset ADE/FDE within 1e-5 relative; raw_data_dict trajectories within 1e-5."""
+    import social_stgcnn_b200 as sstg
+    from social_stgcnn_b200 import driver
+    from social_stgcnn_b200.utils import TrajectoryDataset
+    d = TrajectoryDataset(os.path.join(GOLD, "datasets", "eth", "test") + "/", obs_len=8, pred_len=12, skip=1,
+                          norm_lap_matr=True, device=dev)
+    params, bn = golden.params("eth")
+    eng = sstg.InferenceEngine(params, bn, dev)
+    eps = np.concatenate([golden.sample[f"eth{i:03d}.eps"].reshape(-1) for i in range(70)]).astype(np.float32)
+    ade_, fde_, raw = driver.evaluate(d, eng, KSTEPS=20, eps=torch.from_numpy(eps).to(dev), want_raw=True)
+    ra, rf = float(golden.sample["eth.ade"][0]), float(golden.sample["eth.fde"][0])
+    assert abs(ade_ - ra) < 1e-5 * ra and abs(fde_ - rf) < 1e-5 * rf, (ade_, ra, fde_, rf)
+    assert sorted(raw) == list(range(1, 71))
+    for i in (0, 17, 69):
+        name = f"eth{i:03d}"
+        got = np.stack(raw[i + 1]["pred"])
+        assert got.shape == golden.sample[f"{name}.pred_abs"].shape
+        assert rel_err(got, golden.sample[f"{name}.pred_abs"]) < 1e-5, name
+        assert np.array_equal(raw[i + 1]["obs"][-1], golden.graph[f"{name}.obs"][:, :, -1]) or \
+            rel_err(raw[i + 1]["obs"][-1], golden.graph[f"{name}.obs"][:, :, -1]) < 1e-6
+    # Philox mode: statistically the same score (eth/test unseeded reference run: 0.73 / 1.22)
+    a2, f2, _ = driver.evaluate(d, eng, KSTEPS=20, seed=3)
+    assert 0.6 < a2 < 0.9 and 1.0 < f2 < 1.5
+
+
+def test_driver_train_epoch_vs_oracle(golden, dev):
+    """driver.train_epoch (two optimiser groups of 4 on the first 8 eth/test scenes, lr 0.01)
+    against the oracle replaying train.py's loop with SGD: returned loss, final weights, BN."""
+    import social_stgcnn_b200 as sstg
+    from oracle import stgcnn_oracle as O
+    from social_stgcnn_b200 import driver
+    from social_stgcnn_b200.utils import TrajectoryDataset
+    d = TrajectoryDataset(os.path.join(GOLD, "datasets", "eth", "test") + "/", obs_len=8, pred_len=12, skip=1,
+                          norm_lap_matr=True, device=dev)
+    params, bn = golden.params("eth")
+    eng = sstg.TrainEngine(params, bn, dev)
+    order = np.arange(8)
+
+    class _Sub:                                       # the first 8 scenes as an "epoch"
+        packed, plan_obs = d.packed, d.plan_obs
+        def __len__(self):
+            return 8
+    got = driver.train_epoch(_Sub(), eng, batch_size=4, lr=0.01, order=order)
+    torch.cuda.synchronize()
+    P, S = O.unflatten_params(params), O.unflatten_bn(bn)
+    flat = params.astype(np.float32).copy()
+    tot = 0.0
+    for g0 in (0, 4):
+        scenes = []
+        for i in range(g0, g0 + 4):
+            g = golden.graph
+            scenes.append((g[f"eth{i:03d}.V_obs"], g[f"eth{i:03d}.A_obs"], g[f"eth{i:03d}.V_tr"]))
+        lo, go, S, _ = O.train_step(O.unflatten_params(flat), S, scenes, 4)
+        flat = (flat - np.float32(0.01) * go).astype(np.float32)
+        tot += lo
+    assert abs(got - tot / 8) < 1e-5 * max(1.0, abs(tot / 8)), (got, tot / 8)
+    w = eng.params.cpu().numpy()
+    assert np.abs(w - flat).max() < 1e-5 * np.abs(flat).max()
+    assert np.allclose(eng.bn.cpu().numpy(), O.flatten_bn(S), rtol=1e-5, atol=1e-7)
+    assert eng.num_batches_tracked == 8
