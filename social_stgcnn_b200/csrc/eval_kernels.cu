@@ -18,6 +18,8 @@
 // or draws the noise in-kernel with Philox4x32-10 + Box-Muller.
 //
 // (4a) replaces metrics.bivariate_loss (metrics.py:84-113), one warp per scene.
+#include <type_traits>
+
 #include "sstg_common.cuh"
 
 namespace sstg {
@@ -43,11 +45,19 @@ struct Philox {
   }
 };
 
-// two standard normals from two uint32 (Box-Muller on (0,1) uniforms)
+// two standard normals from two uint32 (Box-Muller).  u1 in (0,1], u2 in [0,1) are built from
+// the top 23 bits with the exponent trick (no int->float conversion), the transcendental part
+// is three MUFU ops (lg2, sqrt, sin/cos approx) -- the noise only has to be N(0,1), and
+// tests/philox_ref.py replays exactly this recipe.
+__device__ __forceinline__ float sqrt_approx(float x) {
+  float y;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ float2 box_muller(uint32_t a, uint32_t b) {
-  const float u1 = (static_cast<float>(a >> 8) + 0.5f) * (1.0f / 16777216.0f);
-  const float u2 = (static_cast<float>(b >> 8) + 0.5f) * (1.0f / 16777216.0f);
-  const float r = sqrtf(-2.0f * __logf(u1));
+  const float u1 = 2.0f - __uint_as_float((a >> 9) | 0x3f800000u);   // (0, 1]
+  const float u2 = __uint_as_float((b >> 9) | 0x3f800000u) - 1.0f;   // [0, 1)
+  const float r = sqrt_approx(-1.3862943611198906f * __log2f(u1));   // sqrt(-2 ln u1)
   float sn, cs;
   __sincosf(6.283185307179586f * u2, &sn, &cs);
   return make_float2(r * cs, r * sn);
@@ -63,15 +73,22 @@ __device__ __forceinline__ int find_scene(const int32_t* __restrict__ seg_off, i
   return lo;
 }
 
-template <bool FP64_DIST>
-__global__ void __launch_bounds__(E_THREADS)
+constexpr int E_KU = 5;  // samples a thread advances together (K = 20 -> one pass of 4 x 5)
+
+// EXACT  : the reference's rounding points (separately rounded mean + L eps, fp64 sqrt and
+//          fp64 sequential sum of the 12 distances, metrics.py:33-34,50); otherwise fp32 with FMA.
+// PHILOX : draw the noise in-kernel instead of reading eps.
+// EXTRA  : eps_out / pred_abs requested (raw_data_dict, test.py:105).
+template <bool EXACT, bool PHILOX, bool EXTRA>
+__global__ void __launch_bounds__(E_THREADS, 2)
 sample_ade_fde_kernel(const float* __restrict__ Vpred, const float* __restrict__ Vtr,
                       const float* __restrict__ last_obs, const int32_t* __restrict__ seg_off, int S, int K,
                       const float* __restrict__ eps, uint64_t seed, float* __restrict__ eps_out,
                       double* __restrict__ min_ade, double* __restrict__ min_fde, float* __restrict__ pred_abs) {
+  using Acc = typename std::conditional<EXACT, double, float>::type;
   // [t][field][ped]: mux, muy, L00, L10, L11, gtx, gty
   __shared__ float par[T_PRED][7][E_PEDS];
-  __shared__ double red[2][E_SUB][E_PEDS];
+  __shared__ Acc red[2][E_SUB][E_PEDS];
   __shared__ int sc_n0[E_PEDS], sc_N[E_PEDS];
   const int tid = threadIdx.x;
   const int P = seg_off[S];
@@ -110,7 +127,9 @@ sample_ade_fde_kernel(const float* __restrict__ Vpred, const float* __restrict__
     par[t][3][pl] = L10;
     par[t][4][pl] = L11;
   }
-  // ---- ground-truth absolute trajectory: sequential fp32 prefix sum + fp64 add of the start
+  // ---- ground-truth absolute trajectory: sequential fp32 prefix sum, then the start position.
+  // metrics.py:69-75 adds the start in fp64 and stores fp32; fp32(fp64(a) + fp64(b)) equals the
+  // fp32 sum (double rounding through a 53 >= 2*24+2 bit format is innocuous), so __fadd_rn is bit-exact.
   if (tid < E_PEDS && sc_N[tid] > 0) {
     const int N = sc_N[tid], n0 = sc_n0[tid], nl = p_base + tid - n0;
     const float2* vt = reinterpret_cast<const float2*>(Vtr) + static_cast<size_t>(n0) * T_PRED + nl;
@@ -121,74 +140,111 @@ sample_ade_fde_kernel(const float* __restrict__ Vpred, const float* __restrict__
       const float2 v = vt[t * N];
       cx = __fadd_rn(cx, v.x);
       cy = __fadd_rn(cy, v.y);
-      par[t][5][tid] = static_cast<float>(static_cast<double>(cx) + static_cast<double>(init.x));
-      par[t][6][tid] = static_cast<float>(static_cast<double>(cy) + static_cast<double>(init.y));
+      par[t][5][tid] = __fadd_rn(cx, init.x);
+      par[t][6][tid] = __fadd_rn(cy, init.y);
     }
   }
   __syncthreads();
 
   const int sub = tid / E_PEDS, pl = tid - sub * E_PEDS;
   const int N = sc_N[pl];
-  double best_a = 1e300, best_f = 1e300;
+  Acc best_a = Acc(3.0e38f), best_f = Acc(3.0e38f);
   if (N > 0) {
     const int p = p_base + pl;
     const int n0 = sc_n0[pl], nl = p - n0;
     const float2 init = reinterpret_cast<const float2*>(last_obs)[p];
-    const double ix = init.x, iy = init.y;
     const size_t eb = static_cast<size_t>(n0) * K * (T_PRED * 2);  // scene block (K,12,N,2)
     const uint2 key = make_uint2(static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32));
-    for (int k = sub; k < K; k += E_SUB) {
-      float cx = 0.f, cy = 0.f;
-      double acc = 0.0, fde = 0.0;
-      float2 e_next = make_float2(0.f, 0.f);
+    for (int kb = sub; kb < K; kb += E_SUB * E_KU) {
+      float cx[E_KU], cy[E_KU];
+      Acc acc[E_KU], fd[E_KU];
 #pragma unroll
-      for (int t = 0; t < T_PRED; ++t) {
-        const size_t ei = eb + (static_cast<size_t>(k * T_PRED + t) * N + nl) * 2;
-        float2 e;
-        if (eps != nullptr) {
-          e = *reinterpret_cast<const float2*>(eps + ei);
-        } else if ((t & 1) == 0) {
-          const uint4 r = Philox::run(make_uint4(static_cast<uint32_t>(k * (T_PRED / 2) + t / 2), 0u,
-                                                 static_cast<uint32_t>(p), 0u), key);
-          e = box_muller(r.x, r.y);
-          e_next = box_muller(r.z, r.w);
-        } else {
-          e = e_next;
-        }
-        if (eps_out != nullptr) *reinterpret_cast<float2*>(eps_out + ei) = e;
-        // sample = mean + L @ eps, separate roundings like the bmm + add of rsample
-        const float sxv = __fadd_rn(par[t][0][pl], __fmul_rn(par[t][2][pl], e.x));
-        const float syv = __fadd_rn(par[t][1][pl],
-                                    __fadd_rn(__fmul_rn(par[t][3][pl], e.x), __fmul_rn(par[t][4][pl], e.y)));
-        cx = __fadd_rn(cx, sxv);
-        cy = __fadd_rn(cy, syv);
-        const float ax = static_cast<float>(static_cast<double>(cx) + ix);
-        const float ay = static_cast<float>(static_cast<double>(cy) + iy);
-        if (pred_abs != nullptr) *reinterpret_cast<float2*>(pred_abs + ei) = make_float2(ax, ay);
-        const float dx = __fsub_rn(ax, par[t][5][pl]);
-        const float dy = __fsub_rn(ay, par[t][6][pl]);
-        const float d2 = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
-        const double d = FP64_DIST ? sqrt(static_cast<double>(d2)) : static_cast<double>(sqrtf(d2));
-        acc += d;
-        if (t == T_PRED - 1) fde = d;
+      for (int i = 0; i < E_KU; ++i) {
+        cx[i] = cy[i] = 0.f;
+        acc[i] = fd[i] = Acc(0);
       }
-      const double ade = acc / static_cast<double>(T_PRED);
-      best_a = ade < best_a ? ade : best_a;
-      best_f = fde < best_f ? fde : best_f;
+#pragma unroll 1
+      for (int tp = 0; tp < T_PRED / 2; ++tp) {  // not unrolled: keeps the 84 shared-memory parameter loads from being hoisted
+        float2 e2[2][E_KU];
+#pragma unroll
+        for (int i = 0; i < E_KU; ++i) {
+          const int k = kb + E_SUB * i;
+          if (PHILOX) {
+            const uint4 r = Philox::run(make_uint4(static_cast<uint32_t>(k * (T_PRED / 2) + tp), 0u,
+                                                   static_cast<uint32_t>(p), 0u), key);
+            e2[0][i] = box_muller(r.x, r.y);
+            e2[1][i] = box_muller(r.z, r.w);
+          } else if (k < K) {
+            const size_t ei = eb + (static_cast<size_t>(k * T_PRED + 2 * tp) * N + nl) * 2;
+            e2[0][i] = *reinterpret_cast<const float2*>(eps + ei);
+            e2[1][i] = *reinterpret_cast<const float2*>(eps + ei + static_cast<size_t>(N) * 2);
+          } else {
+            e2[0][i] = e2[1][i] = make_float2(0.f, 0.f);
+          }
+        }
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          const int t = 2 * tp + hh;
+          const float mux = par[t][0][pl], muy = par[t][1][pl], l00 = par[t][2][pl], l10 = par[t][3][pl],
+                      l11 = par[t][4][pl], gx = par[t][5][pl], gy = par[t][6][pl];
+#pragma unroll
+          for (int i = 0; i < E_KU; ++i) {
+            const float2 e = e2[hh][i];
+            float sxv, syv;
+            if (EXACT) {  // sample = mean + L @ eps with the separate roundings of the bmm + add of rsample
+              sxv = __fadd_rn(mux, __fmul_rn(l00, e.x));
+              syv = __fadd_rn(muy, __fadd_rn(__fmul_rn(l10, e.x), __fmul_rn(l11, e.y)));
+            } else {
+              sxv = fmaf(l00, e.x, mux);
+              syv = fmaf(l11, e.y, fmaf(l10, e.x, muy));
+            }
+            cx[i] = __fadd_rn(cx[i], sxv);
+            cy[i] = __fadd_rn(cy[i], syv);
+            const float ax = __fadd_rn(cx[i], init.x);
+            const float ay = __fadd_rn(cy[i], init.y);
+            if (EXTRA) {
+              const int k = kb + E_SUB * i;
+              if (k < K) {
+                const size_t ei = eb + (static_cast<size_t>(k * T_PRED + t) * N + nl) * 2;
+                if (eps_out != nullptr) *reinterpret_cast<float2*>(eps_out + ei) = e;
+                if (pred_abs != nullptr) *reinterpret_cast<float2*>(pred_abs + ei) = make_float2(ax, ay);
+              }
+            }
+            const float dx = __fsub_rn(ax, gx);
+            const float dy = __fsub_rn(ay, gy);
+            if (EXACT) {
+              const double d = sqrt(static_cast<double>(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy))));
+              acc[i] += d;
+              fd[i] = d;
+            } else {
+              const float d = sqrt_approx(fmaf(dx, dx, dy * dy));
+              acc[i] += d;
+              fd[i] = d;
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < E_KU; ++i)
+        if (kb + E_SUB * i < K) {
+          const Acc ade = acc[i] / Acc(T_PRED);
+          best_a = ade < best_a ? ade : best_a;
+          best_f = fd[i] < best_f ? fd[i] : best_f;
+        }
     }
   }
   red[0][sub][pl] = best_a;
   red[1][sub][pl] = best_f;
   __syncthreads();
   if (tid < E_PEDS && sc_N[tid] > 0) {
-    double a = red[0][0][tid], f = red[1][0][tid];
+    Acc a = red[0][0][tid], f = red[1][0][tid];
 #pragma unroll
     for (int u = 1; u < E_SUB; ++u) {
       a = red[0][u][tid] < a ? red[0][u][tid] : a;
       f = red[1][u][tid] < f ? red[1][u][tid] : f;
     }
-    min_ade[p_base + tid] = a;
-    min_fde[p_base + tid] = f;
+    min_ade[p_base + tid] = static_cast<double>(a);
+    min_fde[p_base + tid] = static_cast<double>(f);
   }
 }
 
@@ -242,12 +298,19 @@ int launch_sample_ade_fde(const float* Vpred, const float* Vtr, const float* las
                           double* min_fde, float* pred_abs, int flags, cudaStream_t st) {
   if (S == 0 || P == 0) return SSTG_OK;
   const int grid = (P + E_PEDS - 1) / E_PEDS;
-  if (flags & SSTG_EVAL_FP64_DIST)
-    sample_ade_fde_kernel<true><<<grid, E_THREADS, 0, st>>>(Vpred, Vtr, last_obs, seg_off, S, K, eps, seed,
-                                                            eps_out, min_ade, min_fde, pred_abs);
-  else
-    sample_ade_fde_kernel<false><<<grid, E_THREADS, 0, st>>>(Vpred, Vtr, last_obs, seg_off, S, K, eps, seed,
-                                                             eps_out, min_ade, min_fde, pred_abs);
+  const bool exact = flags & SSTG_EVAL_FP64_DIST, philox = eps == nullptr;
+  const bool extra = eps_out != nullptr || pred_abs != nullptr;
+#define SSTG_LAUNCH_SAMPLE(EX, PH, XT)                                                                         \
+  sample_ade_fde_kernel<EX, PH, XT><<<grid, E_THREADS, 0, st>>>(Vpred, Vtr, last_obs, seg_off, S, K, eps, seed, \
+                                                                eps_out, min_ade, min_fde, pred_abs)
+  if (exact) {
+    if (philox) { if (extra) SSTG_LAUNCH_SAMPLE(true, true, true); else SSTG_LAUNCH_SAMPLE(true, true, false); }
+    else        { if (extra) SSTG_LAUNCH_SAMPLE(true, false, true); else SSTG_LAUNCH_SAMPLE(true, false, false); }
+  } else {
+    if (philox) { if (extra) SSTG_LAUNCH_SAMPLE(false, true, true); else SSTG_LAUNCH_SAMPLE(false, true, false); }
+    else        { if (extra) SSTG_LAUNCH_SAMPLE(false, false, true); else SSTG_LAUNCH_SAMPLE(false, false, false); }
+  }
+#undef SSTG_LAUNCH_SAMPLE
   SSTG_CUDA_TRY(cudaGetLastError(), "sample_ade_fde launch");
   return SSTG_OK;
 }

@@ -168,6 +168,171 @@ graph_build_kernel(const float* __restrict__ rel, const int32_t* __restrict__ se
   }
 }
 
+// ---------------------------------------------------------------------------------------
+// Fast path (fp32, normalised Laplacian, N <= 64): every weight is computed ONCE.
+// A work item is (scene, group of 4 timesteps); warp <-> timestep.  Pass 1 walks the rows,
+// lanes own columns: w = rsqrt(|d|^2) goes to a per-warp shared W tile while the lane
+// accumulates its column sum (= row sum, W symmetric).  Then ds = rsqrt(1 + sum) and the
+// diagonal of the tile is overwritten with -(d - 1), so that pass 2 is the branch-free
+// A = fma(-(w ds_h), ds_k, +0)  streamed from shared memory as 16-byte rows: full 128-byte
+// store segments, and absent edges come out as +0.0 like the reference's.
+// ---------------------------------------------------------------------------------------
+constexpr int F_WARPS = 4;
+constexpr int F_THREADS = F_WARPS * 32;
+
+template <int NJ>
+__global__ void __launch_bounds__(F_THREADS)
+graph_build_fast_kernel(const float* __restrict__ rel, const int32_t* __restrict__ seg_off,
+                        const int64_t* __restrict__ a_off, int S, int T, int NP, int wtile,
+                        float* __restrict__ V, float* __restrict__ A) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float* xs = reinterpret_cast<float*>(smem_raw);   // [4][NP]
+  float* ys = xs + F_WARPS * NP;                    // [4][NP]
+  float* dsm = ys + F_WARPS * NP;                   // [4][NP]
+  float* Wt = dsm + F_WARPS * NP + static_cast<size_t>(threadIdx.x >> 5) * wtile;  // [warp][N*N]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int groups = (T + F_WARPS - 1) / F_WARPS;
+  const long long items = static_cast<long long>(S) * groups;
+
+  for (long long it = blockIdx.x; it < items; it += gridDim.x) {
+    const int s = static_cast<int>(it / groups);
+    const int t0 = static_cast<int>(it - static_cast<long long>(s) * groups) * F_WARPS;
+    const int n0 = seg_off[s];
+    const int N = seg_off[s + 1] - n0;
+    const float* r = rel + static_cast<size_t>(n0) * 2 * T;
+    const int nt = (T - t0 < F_WARPS) ? (T - t0) : F_WARPS;
+    // rel (N,2,T) -> xs/ys[tt][p] for the group's timesteps
+    if ((T & 3) == 0) {
+      for (int i = tid; i < 2 * N; i += F_THREADS) {  // i = p*2 + c: one 16-byte run of 4 timesteps
+        const float4 v = *reinterpret_cast<const float4*>(r + static_cast<size_t>(i) * T + t0);
+        float* dst = ((i & 1) ? ys : xs) + (i >> 1);
+        dst[0] = v.x;
+        dst[NP] = v.y;
+        dst[2 * NP] = v.z;
+        dst[3 * NP] = v.w;
+      }
+    } else {
+      for (int i = tid; i < 2 * N * nt; i += F_THREADS) {
+        const int pc = i / nt, tt = i - pc * nt;
+        ((pc & 1) ? ys : xs)[tt * NP + (pc >> 1)] = r[static_cast<size_t>(pc) * T + t0 + tt];
+      }
+    }
+    __syncthreads();
+    float2* Vs = reinterpret_cast<float2*>(V + static_cast<size_t>(n0) * T * 2) + static_cast<size_t>(t0) * N;
+    for (int i = tid; i < N * nt; i += F_THREADS) {
+      const int tt = i / N, pp = i - tt * N;
+      Vs[i] = make_float2(xs[tt * NP + pp], ys[tt * NP + pp]);
+    }
+    if (warp < nt) {
+      const float* xt = xs + warp * NP;
+      const float* yt = ys + warp * NP;
+      float* dst = dsm + warp * NP;
+      float xk[NJ], yk[NJ], acc[NJ][2];
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) {
+        const int k = lane + 32 * j;
+        xk[j] = k < N ? xt[k] : 0.f;
+        yk[j] = k < N ? yt[k] : 0.f;
+        acc[j][0] = acc[j][1] = 0.f;
+      }
+      // ---- pass 1: weights once, column sums on the fly
+      int h = 0;
+      for (; h + 2 <= N; h += 2) {
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const float xh = xt[h + u], yh = yt[h + u];
+#pragma unroll
+          for (int j = 0; j < NJ; ++j) {
+            const float dx = xh - xk[j], dy = yh - yk[j];
+            const float sq = fmaf(dx, dx, dy * dy);
+            const float w = sq > 0.f ? rsqrtf(sq) : 0.f;
+            acc[j][u] += w;
+            if (lane + 32 * j < N) Wt[(h + u) * N + lane + 32 * j] = w;
+          }
+        }
+      }
+      if (h < N) {
+        const float xh = xt[h], yh = yt[h];
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+          const float dx = xh - xk[j], dy = yh - yk[j];
+          const float sq = fmaf(dx, dx, dy * dy);
+          const float w = sq > 0.f ? rsqrtf(sq) : 0.f;
+          acc[j][0] += w;
+          if (lane + 32 * j < N) Wt[h * N + lane + 32 * j] = w;
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) {
+        const int k = lane + 32 * j;
+        const float lkk = acc[j][0] + acc[j][1];  // the diagonal contributed w(0) = 0: d = 1 + off-diagonal sum
+        if (k < N) {
+          dst[k] = rsqrtf(1.f + lkk);
+          Wt[k * N + k] = -lkk;  // so that -(W_kk) ds_k ds_k = (d_k - 1) / d_k
+        }
+      }
+      __syncwarp();
+      // ---- pass 2: A_hk = -(w_hk ds_h) ds_k, streamed out
+      float* At = A + a_off[s] + static_cast<size_t>(t0 + warp) * N * N;
+      if ((N & 3) == 0) {
+        const int lpr = N >> 2;            // 16-byte chunks per row (<= 16 for N <= 64)
+        const int rpp = 32 / lpr;          // rows per warp pass
+        const int rr = lane / lpr, c4 = (lane - rr * lpr) * 4;
+        const float4 dk = *reinterpret_cast<const float4*>(dst + c4);
+        if (rr < rpp) {
+          for (int hh = rr; hh < N; hh += rpp) {
+            const float4 w4 = *reinterpret_cast<const float4*>(Wt + hh * N + c4);
+            const float dh = dst[hh];
+            float4 o;
+            o.x = fmaf(-(w4.x * dh), dk.x, 0.f);
+            o.y = fmaf(-(w4.y * dh), dk.y, 0.f);
+            o.z = fmaf(-(w4.z * dh), dk.z, 0.f);
+            o.w = fmaf(-(w4.w * dh), dk.w, 0.f);
+            *reinterpret_cast<float4*>(At + static_cast<size_t>(hh) * N + c4) = o;
+          }
+        }
+      } else {
+        float dk[NJ];
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) dk[j] = (lane + 32 * j < N) ? dst[lane + 32 * j] : 0.f;
+        for (int hh = 0; hh < N; ++hh) {
+          const float dh = dst[hh];
+#pragma unroll
+          for (int j = 0; j < NJ; ++j) {
+            const int k = lane + 32 * j;
+            if (k < N) At[static_cast<size_t>(hh) * N + k] = fmaf(-(Wt[hh * N + k] * dh), dk[j], 0.f);
+          }
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
+template <int NJ>
+int launch_fast(const float* rel, const int32_t* seg_off, const int64_t* a_off, int S, int T, int max_n, float* V,
+                float* A, cudaStream_t st) {
+  const int NP = (max_n + 3) & ~3;
+  const int wtile = (max_n * max_n + 3) & ~3;
+  const size_t smem = sizeof(float) * (static_cast<size_t>(3 * F_WARPS * NP) + static_cast<size_t>(F_WARPS) * wtile);
+  auto kern = graph_build_fast_kernel<NJ>;
+  if (smem > 48 * 1024)
+    SSTG_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)),
+                  "graph_build_fast smem attr");
+  int dev = 0, sms = 148;
+  SSTG_CUDA_TRY(cudaGetDevice(&dev), "cudaGetDevice");
+  SSTG_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev), "sm count");
+  int per_sm = 1;
+  SSTG_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, F_THREADS, smem), "occupancy");
+  if (per_sm < 1) per_sm = 1;
+  const long long items = static_cast<long long>(S) * ((T + F_WARPS - 1) / F_WARPS);
+  const long long want = static_cast<long long>(sms) * per_sm;
+  const int grid = static_cast<int>(items < want ? items : want);
+  kern<<<grid, F_THREADS, smem, st>>>(rel, seg_off, a_off, S, T, NP, wtile, V, A);
+  SSTG_CUDA_TRY(cudaGetLastError(), "graph_build_fast launch");
+  return SSTG_OK;
+}
+
 template <bool F64, int NJ>
 int launch_nj(const float* rel, const int32_t* seg_off, const int64_t* a_off, int S, int T, int NP, float* V,
               float* A, int flags, cudaStream_t st) {
@@ -206,6 +371,10 @@ int launch_graph_build(const float* rel, const int32_t* seg_off, const int64_t* 
                        float* V, float* A, int flags, cudaStream_t st) {
   if (S == 0) return SSTG_OK;
   if (flags & SSTG_GRAPH_FP64) return launch_f<true>(rel, seg_off, a_off, S, T, max_n, V, A, flags, st);
+  if ((flags & SSTG_GRAPH_NORM_LAP) && !(flags & SSTG_GRAPH_V_ONLY) && max_n <= 64) {
+    if (max_n <= 32) return launch_fast<1>(rel, seg_off, a_off, S, T, max_n, V, A, st);
+    return launch_fast<2>(rel, seg_off, a_off, S, T, max_n, V, A, st);
+  }
   return launch_f<false>(rel, seg_off, a_off, S, T, max_n, V, A, flags, st);
 }
 

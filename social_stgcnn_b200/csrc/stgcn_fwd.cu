@@ -21,6 +21,8 @@
 //   * BN (eval) is folded into scale/offset pairs once per CTA; the temporal conv needs the
 //     neighbouring timesteps, i.e. other warps' results, through a double-buffered
 //     shared tile and ONE __syncthreads per scene.
+#include <cstdlib>
+
 #include "sstg_common.cuh"
 
 namespace sstg {
@@ -94,8 +96,10 @@ __device__ __forceinline__ void cursor_open(Cursor& c, int s, int S, int t, int 
   }
 }
 
-template <int NJ>
-__global__ void __launch_bounds__(S_THREADS, 1)
+// CPS = CTAs per SM the kernel is compiled for (register cap 255 / 128): two co-resident CTAs
+// (16 warps) hide the shared-memory and mbarrier latencies of each other's math phases.
+template <int NJ, int CPS>
+__global__ void __launch_bounds__(S_THREADS, CPS)
 stgcn_fwd_kernel(const float* __restrict__ V, const float* __restrict__ A, const int32_t* __restrict__ seg_off,
                  const int64_t* __restrict__ a_off, int S, int max_n, const float* __restrict__ params,
                  const float* __restrict__ bn, float* __restrict__ H, int smem_budget) {
@@ -287,24 +291,33 @@ stgcn_fwd_kernel(const float* __restrict__ V, const float* __restrict__ A, const
   }
 }
 
-template <int NJ>
+template <int NJ, int CPS>
 int launch_nj(const float* V, const float* A, const int32_t* seg_off, const int64_t* a_off, int S, int max_n,
               const float* params, const float* bn, float* H, int sm_count, cudaStream_t st) {
   int dev = 0, sms = 148, max_optin = 0;
   SSTG_CUDA_TRY(cudaGetDevice(&dev), "cudaGetDevice");
   SSTG_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev), "sm count");
   SSTG_CUDA_TRY(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev), "smem optin");
-  const int budget = max_optin;  // 227 KB on sm_100
+  // 227 KB for one CTA per SM; two CTAs share the SM's 228 KB (1 KB reserved per CTA)
+  const int budget = CPS == 1 ? max_optin : (max_optin + 1024) / 2 - 1024;
   const SmemLayout L = make_layout(max_n, static_cast<size_t>(budget));
   if (L.chunk_floats < L.NP) return SSTG_ETOOBIG;
-  auto kern = stgcn_fwd_kernel<NJ>;
+  auto kern = stgcn_fwd_kernel<NJ, CPS>;
   SSTG_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(L.total)),
                 "stgcn smem attr");
   if (sm_count > 0 && sm_count < sms) sms = sm_count;
-  const int grid = S < sms ? S : sms;
+  const long long want = static_cast<long long>(sms) * CPS;
+  const int grid = static_cast<int>(S < want ? S : want);
   kern<<<grid, S_THREADS, L.total, st>>>(V, A, seg_off, a_off, S, max_n, params, bn, H, budget);
   SSTG_CUDA_TRY(cudaGetLastError(), "stgcn launch");
   return SSTG_OK;
+}
+
+// SSTG_STGCN_CPS=1|2 overrides the CTAs-per-SM choice (tuning knob; default 2 for N <= 64).
+int stgcn_cps_default(int max_n) {
+  const char* e = getenv("SSTG_STGCN_CPS");
+  if (e && (e[0] == '1' || e[0] == '2')) return e[0] - '0';
+  return max_n <= 64 ? 2 : 1;
 }
 
 }  // namespace
@@ -313,10 +326,15 @@ int launch_stgcn_forward(const float* V, const float* A, const int32_t* seg_off,
                          int max_n, const float* params, const float* bn, float* H, int sm_count,
                          cudaStream_t st) {
   if (S == 0) return SSTG_OK;
-  if (max_n <= 32) return launch_nj<1>(V, A, seg_off, a_off, S, max_n, params, bn, H, sm_count, st);
-  if (max_n <= 64) return launch_nj<2>(V, A, seg_off, a_off, S, max_n, params, bn, H, sm_count, st);
-  if (max_n <= 128) return launch_nj<4>(V, A, seg_off, a_off, S, max_n, params, bn, H, sm_count, st);
-  return launch_nj<8>(V, A, seg_off, a_off, S, max_n, params, bn, H, sm_count, st);
+  const bool two = stgcn_cps_default(max_n) == 2 && max_n <= 64;
+  if (max_n <= 32)
+    return two ? launch_nj<1, 2>(V, A, seg_off, a_off, S, max_n, params, bn, H, sm_count, st)
+               : launch_nj<1, 1>(V, A, seg_off, a_off, S, max_n, params, bn, H, sm_count, st);
+  if (max_n <= 64)
+    return two ? launch_nj<2, 2>(V, A, seg_off, a_off, S, max_n, params, bn, H, sm_count, st)
+               : launch_nj<2, 1>(V, A, seg_off, a_off, S, max_n, params, bn, H, sm_count, st);
+  if (max_n <= 128) return launch_nj<4, 1>(V, A, seg_off, a_off, S, max_n, params, bn, H, sm_count, st);
+  return launch_nj<8, 1>(V, A, seg_off, a_off, S, max_n, params, bn, H, sm_count, st);
 }
 
 }  // namespace sstg

@@ -47,7 +47,7 @@ txpcnn_fwd_kernel(const float* __restrict__ Hin, const int32_t* __restrict__ seg
   const int half = tid / X_COLS;  // warp-uniform
   const int qt = tid - half * X_COLS;
 
-  // ---- weights: params [co][ci][3][3] -> shared [layer][ci][half][co%6][9]
+  // ---- weights: params [co][ci][3][3] -> shared [layer][ci][half][tap][co%6]  (tap-major for FFMA2 pairs)
   for (int i = tid; i < X_WTOTAL; i += X_THREADS) {
     int l, r;
     if (i < X_W0) {
@@ -61,7 +61,7 @@ txpcnn_fwd_kernel(const float* __restrict__ Hin, const int32_t* __restrict__ seg
     const int hf = r2 / X_WSLOT, r3 = r2 % X_WSLOT;
     float v = 0.f;
     if (r3 < 54) {
-      const int co = hf * 6 + r3 / 9, tap = r3 % 9;
+      const int co = hf * 6 + r3 % 6, tap = r3 / 6;
       const int cin = (l == 0) ? 8 : 12;
       const int base = (l == 0) ? P_TP0_W : (l == 4 ? P_TPOUT_W : P_TP1_W + (l - 1) * P_TP_STRIDE);
       v = params[base + (co * cin + ci) * 9 + tap];
@@ -97,11 +97,16 @@ txpcnn_fwd_kernel(const float* __restrict__ Hin, const int32_t* __restrict__ seg
     }
     __syncthreads();
     // ---- load the 40 input rows of every scene of the tile (coalesced along the pedestrian axis)
+    // thread = (column, row parity): 20 independent 4-byte cp.async in flight per thread, no index division
     const float* Hb = Hin + static_cast<size_t>(p_lo) * 40;
-    for (int i = tid; i < 40 * cols; i += X_THREADS) {
-      const int row = i / cols, q = i - row * cols;
-      act[row * Wp + sm.scol[q]] = Hb[sm.goff[q] + row * sm.nstr[q]];
+    for (int q = tid & (X_COLS - 1); q < cols; q += X_COLS) {
+      const float* src = Hb + sm.goff[q];
+      float* dst = act + sm.scol[q];
+      const int ns = sm.nstr[q];
+#pragma unroll
+      for (int row = tid >> 7; row < 40; row += X_THREADS / X_COLS) cp_async4(dst + row * Wp, src + row * ns);
     }
+    cp_async_wait_all();
     __syncthreads();
 
     int sc[JX], gN[JX];
@@ -120,21 +125,21 @@ txpcnn_fwd_kernel(const float* __restrict__ Hin, const int32_t* __restrict__ seg
 
 #pragma unroll 1
     for (int l = 0; l < 5; ++l) {
-      float acc[JX][6][5];
+      float2 acc[JX][3][5];  // [column][channel pair][feature row]
       const float* wl = sm.w + (l == 0 ? 0 : X_W0 + (l - 1) * X_WL);
 #pragma unroll
       for (int u = 0; u < JX; ++u) {
 #pragma unroll
-        for (int co = 0; co < 6; ++co) {
-          const float b = sm.bias[l][half * 6 + co];
+        for (int pr = 0; pr < 3; ++pr) {
+          const float2 b = make_float2(sm.bias[l][half * 6 + 2 * pr], sm.bias[l][half * 6 + 2 * pr + 1]);
 #pragma unroll
-          for (int h = 0; h < 5; ++h) acc[u][co][h] = b;
+          for (int h = 0; h < 5; ++h) acc[u][pr][h] = b;
         }
         if (on[u]) {
           if (l == 0)
-            conv_column<8>(act, Wp, sc[u], wl, half, acc[u]);
+            conv_column2<8>(act, Wp, sc[u], wl, half, acc[u]);
           else
-            conv_column<12>(act, Wp, sc[u], wl, half, acc[u]);
+            conv_column2<12>(act, Wp, sc[u], wl, half, acc[u]);
         }
       }
       if (l < 4) {
@@ -142,26 +147,33 @@ txpcnn_fwd_kernel(const float* __restrict__ Hin, const int32_t* __restrict__ seg
 #pragma unroll
         for (int u = 0; u < JX; ++u)
 #pragma unroll
-          for (int co = 0; co < 6; ++co)
+          for (int pr = 0; pr < 3; ++pr)
 #pragma unroll
-            for (int h = 0; h < 5; ++h) {
-              float v = prelu(acc[u][co][h], sl);
-              if (l > 0) v += act[((half * 6 + co) * 5 + h) * Wp + sc[u]];  // residual (model.py:192)
-              if (SAVE && on[u]) {
-                const long long g = l * layer_stride + gO[u] + static_cast<long long>((half * 6 + co) * 5 + h) * gN[u];
-                Usave[g] = acc[u][co][h];
-                Xsave[g] = v;
+            for (int h = 0; h < 5; ++h)
+#pragma unroll
+              for (int e = 0; e < 2; ++e) {
+                float& a = e ? acc[u][pr][h].y : acc[u][pr][h].x;
+                const int row = (half * 6 + 2 * pr + e) * 5 + h;
+                float v = prelu(a, sl);
+                if (l > 0) v += act[row * Wp + sc[u]];  // residual (model.py:192)
+                if (SAVE && on[u]) {
+                  const long long g = l * layer_stride + gO[u] + static_cast<long long>(row) * gN[u];
+                  Usave[g] = a;
+                  Xsave[g] = v;
+                }
+                a = v;
               }
-              acc[u][co][h] = v;
-            }
         __syncthreads();  // everyone has read the old activations
 #pragma unroll
         for (int u = 0; u < JX; ++u)
           if (on[u])
 #pragma unroll
-            for (int co = 0; co < 6; ++co)
+            for (int pr = 0; pr < 3; ++pr)
 #pragma unroll
-              for (int h = 0; h < 5; ++h) act[((half * 6 + co) * 5 + h) * Wp + sc[u]] = acc[u][co][h];
+              for (int h = 0; h < 5; ++h) {
+                act[((half * 6 + 2 * pr) * 5 + h) * Wp + sc[u]] = acc[u][pr][h].x;
+                act[((half * 6 + 2 * pr + 1) * 5 + h) * Wp + sc[u]] = acc[u][pr][h].y;
+              }
         __syncthreads();
       } else {
 #pragma unroll
@@ -169,9 +181,12 @@ txpcnn_fwd_kernel(const float* __restrict__ Hin, const int32_t* __restrict__ seg
           if (on[u]) {
             float* o = out + gO[u];
 #pragma unroll
-            for (int co = 0; co < 6; ++co)
+            for (int pr = 0; pr < 3; ++pr)
 #pragma unroll
-              for (int h = 0; h < 5; ++h) o[((half * 6 + co) * 5 + h) * gN[u]] = acc[u][co][h];
+              for (int h = 0; h < 5; ++h) {
+                o[((half * 6 + 2 * pr) * 5 + h) * gN[u]] = acc[u][pr][h].x;
+                o[((half * 6 + 2 * pr + 1) * 5 + h) * gN[u]] = acc[u][pr][h].y;
+              }
           }
       }
     }

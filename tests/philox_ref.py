@@ -1,5 +1,6 @@
 """numpy replica of the kernel's noise stream: Philox4x32-10 keyed by the seed, counter
-(k*6 + t//2, 0, pedestrian, 0), Box-Muller on (0,1) uniforms built from the top 24 bits."""
+(k*6 + t//2, 0, pedestrian, 0), Box-Muller on uniforms built from the top 23 bits with the
+exponent trick: u1 = 2 - float(0x3f800000 | a >> 9) in (0, 1], u2 = float(0x3f800000 | b >> 9) - 1."""
 import numpy as np
 
 M0, M1, W0, W1 = 0xD2511F53, 0xCD9E8D57, 0x9E3779B9, 0xBB67AE85
@@ -21,9 +22,10 @@ def philox4x32_10(ctr, key):
 
 
 def _box_muller(a, b):
-    u1 = ((a >> np.uint32(8)).astype(np.float32) + np.float32(0.5)) * np.float32(1.0 / 16777216.0)
-    u2 = ((b >> np.uint32(8)).astype(np.float32) + np.float32(0.5)) * np.float32(1.0 / 16777216.0)
-    r = np.sqrt(np.float32(-2.0) * np.log(u1.astype(np.float64))).astype(np.float32)
+    one_two = lambda x: ((x >> np.uint32(9)) | np.uint32(0x3F800000)).view(np.float32)      # [1, 2)
+    u1 = np.float32(2.0) - one_two(a)
+    u2 = one_two(b) - np.float32(1.0)
+    r = np.sqrt(np.float64(-1.3862943611198906) * np.log2(u1.astype(np.float64))).astype(np.float32)
     ang = (np.float32(6.283185307179586) * u2).astype(np.float64)
     return (r * np.cos(ang)).astype(np.float32), (r * np.sin(ang)).astype(np.float32)
 
