@@ -251,3 +251,25 @@ def test_philox_noise_statistics_and_replay(golden, batch, dev):
         ref = philox_normals(1234, np.arange(o, o + n), 20)          # (K,12,n,2)
         got = e1[o * 480:(o + n) * 480].reshape(20, 12, n, 2)
         assert np.abs(got - ref).max() < 2e-4
+
+
+def test_infer_host_pipelined_chunks_equal_direct_calls(golden, batch, dev):
+    """InferenceEngine.infer_host (host buffers, 3-stream software pipeline over chunks of scenes)
+    returns exactly what direct device-resident calls on the same chunks return."""
+    import social_stgcnn_b200 as sstg
+    plan = batch["plan"]
+    params, bn = golden.params("eth")
+    eng = sstg.InferenceEngine(params, bn, dev)
+    obs_h = batch["obs_rel"].cpu().pin_memory()
+    pred_h = batch["pred_rel"].cpu().pin_memory()
+    last_h = batch["last_obs"].cpu().pin_memory()
+    for chunk in (7, 32, 10 ** 6):
+        a_h, f_h = eng.infer_host(plan, obs_h, pred_h, last_h, 20, chunk_scenes=chunk, seed=5)
+        a_h, f_h = a_h.copy(), f_h.copy()
+        for i, (lo, hi, p_lo, p_hi, sub) in enumerate(plan.chunks(chunk)):
+            r = eng.infer(sub, batch["obs_rel"][p_lo:p_hi].contiguous(), batch["pred_rel"][p_lo:p_hi].contiguous(),
+                          batch["last_obs"][p_lo:p_hi].contiguous(), 20, seed=5 + 0x9E3779B1 * i)
+            torch.cuda.synchronize()
+            assert np.array_equal(a_h[p_lo:p_hi], r["min_ade"].cpu().numpy()), (chunk, i)
+            assert np.array_equal(f_h[p_lo:p_hi], r["min_fde"].cpu().numpy()), (chunk, i)
+    assert len(plan.chunks(7)) == (plan.S + 6) // 7
