@@ -180,6 +180,16 @@ graph_build_kernel(const float* __restrict__ rel, const int32_t* __restrict__ se
 constexpr int F_WARPS = 4;
 constexpr int F_THREADS = F_WARPS * 32;
 
+__device__ __forceinline__ float rsqrt_fast(float x) {
+  float y;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// inverse distance from the squared distance; a squared distance below FLT_MIN (only the
+// exact-zero case occurs with real coordinates) is the reference's "distance 0 -> weight 0"
+__device__ __forceinline__ float inv_dist(float sq) { return sq >= 1.17549435e-38f ? rsqrt_fast(sq) : 0.f; }
+
+// Requires T % 4 == 0 (8 and 12 in every configuration) and N <= 64.
 template <int NJ>
 __global__ void __launch_bounds__(F_THREADS)
 graph_build_fast_kernel(const float* __restrict__ rel, const int32_t* __restrict__ seg_off,
@@ -191,116 +201,155 @@ graph_build_fast_kernel(const float* __restrict__ rel, const int32_t* __restrict
   float* dsm = ys + F_WARPS * NP;                   // [4][NP]
   float* Wt = dsm + F_WARPS * NP + static_cast<size_t>(threadIdx.x >> 5) * wtile;  // [warp][N*N]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int groups = (T + F_WARPS - 1) / F_WARPS;
+  const int groups = T / F_WARPS;
   const long long items = static_cast<long long>(S) * groups;
 
-  for (long long it = blockIdx.x; it < items; it += gridDim.x) {
-    const int s = static_cast<int>(it / groups);
-    const int t0 = static_cast<int>(it - static_cast<long long>(s) * groups) * F_WARPS;
-    const int n0 = seg_off[s];
-    const int N = seg_off[s + 1] - n0;
-    const float* r = rel + static_cast<size_t>(n0) * 2 * T;
-    const int nt = (T - t0 < F_WARPS) ? (T - t0) : F_WARPS;
-    // rel (N,2,T) -> xs/ys[tt][p] for the group's timesteps
-    if ((T & 3) == 0) {
-      for (int i = tid; i < 2 * N; i += F_THREADS) {  // i = p*2 + c: one 16-byte run of 4 timesteps
-        const float4 v = *reinterpret_cast<const float4*>(r + static_cast<size_t>(i) * T + t0);
-        float* dst = ((i & 1) ? ys : xs) + (i >> 1);
-        dst[0] = v.x;
-        dst[NP] = v.y;
-        dst[2 * NP] = v.z;
-        dst[3 * NP] = v.w;
-      }
-    } else {
-      for (int i = tid; i < 2 * N * nt; i += F_THREADS) {
-        const int pc = i / nt, tt = i - pc * nt;
-        ((pc & 1) ? ys : xs)[tt * NP + (pc >> 1)] = r[static_cast<size_t>(pc) * T + t0 + tt];
-      }
+  // software pipeline: the (<= 128) float4 of the NEXT item's displacements and its offsets are
+  // fetched into registers while the current item is computed
+  long long it = blockIdx.x;
+  int s = 0, t0 = 0, n0 = 0, N = 0;
+  long long ao = 0;
+  float4 pre = make_float4(0.f, 0.f, 0.f, 0.f);
+  auto fetch = [&](long long item) {
+    s = static_cast<int>(item / groups);
+    t0 = static_cast<int>(item - static_cast<long long>(s) * groups) * F_WARPS;
+    n0 = seg_off[s];
+    N = seg_off[s + 1] - n0;
+    ao = a_off[s];
+    if (tid < 2 * N)  // tid = p*2 + c: one 16-byte run of 4 timesteps
+      pre = *reinterpret_cast<const float4*>(rel + (static_cast<size_t>(n0) * 2 + tid) * T + t0);
+  };
+  if (it < items) fetch(it);
+
+  while (it < items) {
+    const int cs = s, ct0 = t0, cn0 = n0, cN = N;
+    const long long cao = ao;
+    (void)cs;
+    if (tid < 2 * cN) {
+      float* dst = ((tid & 1) ? ys : xs) + (tid >> 1);
+      dst[0] = pre.x;
+      dst[NP] = pre.y;
+      dst[2 * NP] = pre.z;
+      dst[3 * NP] = pre.w;
     }
     __syncthreads();
-    float2* Vs = reinterpret_cast<float2*>(V + static_cast<size_t>(n0) * T * 2) + static_cast<size_t>(t0) * N;
-    for (int i = tid; i < N * nt; i += F_THREADS) {
-      const int tt = i / N, pp = i - tt * N;
+    it += gridDim.x;
+    if (it < items) fetch(it);
+
+    float2* Vs = reinterpret_cast<float2*>(V + static_cast<size_t>(cn0) * T * 2) + static_cast<size_t>(ct0) * cN;
+    for (int i = tid; i < cN * F_WARPS; i += F_THREADS) {
+      const int tt = i / cN, pp = i - tt * cN;
       Vs[i] = make_float2(xs[tt * NP + pp], ys[tt * NP + pp]);
     }
-    if (warp < nt) {
+    {
       const float* xt = xs + warp * NP;
       const float* yt = ys + warp * NP;
       float* dst = dsm + warp * NP;
       float xk[NJ], yk[NJ], acc[NJ][2];
+      bool kv[NJ];
 #pragma unroll
       for (int j = 0; j < NJ; ++j) {
         const int k = lane + 32 * j;
-        xk[j] = k < N ? xt[k] : 0.f;
-        yk[j] = k < N ? yt[k] : 0.f;
+        kv[j] = k < cN;
+        xk[j] = kv[j] ? xt[k] : 0.f;
+        yk[j] = kv[j] ? yt[k] : 0.f;
         acc[j][0] = acc[j][1] = 0.f;
       }
-      // ---- pass 1: weights once, column sums on the fly
+      // ---- pass 1: weights once, column sums on the fly (4 rows per iteration)
+      float* wp = Wt + lane;
       int h = 0;
-      for (; h + 2 <= N; h += 2) {
+      for (; h + 4 <= cN; h += 4) {
+        const float4 xh = *reinterpret_cast<const float4*>(xt + h);
+        const float4 yh = *reinterpret_cast<const float4*>(yt + h);
+        const float xa[4] = {xh.x, xh.y, xh.z, xh.w}, ya[4] = {yh.x, yh.y, yh.z, yh.w};
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
-          const float xh = xt[h + u], yh = yt[h + u];
+        for (int u = 0; u < 4; ++u) {
 #pragma unroll
           for (int j = 0; j < NJ; ++j) {
-            const float dx = xh - xk[j], dy = yh - yk[j];
-            const float sq = fmaf(dx, dx, dy * dy);
-            const float w = sq > 0.f ? rsqrtf(sq) : 0.f;
-            acc[j][u] += w;
-            if (lane + 32 * j < N) Wt[(h + u) * N + lane + 32 * j] = w;
+            const float dx = xa[u] - xk[j], dy = ya[u] - yk[j];
+            const float w = inv_dist(fmaf(dx, dx, dy * dy));
+            acc[j][u & 1] += w;
+            if (kv[j]) wp[32 * j] = w;
           }
+          wp += cN;
         }
       }
-      if (h < N) {
+      for (; h < cN; ++h) {
         const float xh = xt[h], yh = yt[h];
 #pragma unroll
         for (int j = 0; j < NJ; ++j) {
           const float dx = xh - xk[j], dy = yh - yk[j];
-          const float sq = fmaf(dx, dx, dy * dy);
-          const float w = sq > 0.f ? rsqrtf(sq) : 0.f;
+          const float w = inv_dist(fmaf(dx, dx, dy * dy));
           acc[j][0] += w;
-          if (lane + 32 * j < N) Wt[h * N + lane + 32 * j] = w;
+          if (kv[j]) wp[32 * j] = w;
         }
+        wp += cN;
       }
 #pragma unroll
       for (int j = 0; j < NJ; ++j) {
         const int k = lane + 32 * j;
         const float lkk = acc[j][0] + acc[j][1];  // the diagonal contributed w(0) = 0: d = 1 + off-diagonal sum
-        if (k < N) {
-          dst[k] = rsqrtf(1.f + lkk);
-          Wt[k * N + k] = -lkk;  // so that -(W_kk) ds_k ds_k = (d_k - 1) / d_k
+        if (kv[j]) {
+          dst[k] = rsqrt_fast(1.f + lkk);
+          Wt[k * cN + k] = -lkk;  // so that -(W_kk) ds_k ds_k = (d_k - 1) / d_k
         }
       }
       __syncwarp();
       // ---- pass 2: A_hk = -(w_hk ds_h) ds_k, streamed out
-      float* At = A + a_off[s] + static_cast<size_t>(t0 + warp) * N * N;
-      if ((N & 3) == 0) {
-        const int lpr = N >> 2;            // 16-byte chunks per row (<= 16 for N <= 64)
+      float* At = A + cao + static_cast<size_t>(ct0 + warp) * cN * cN;
+      if ((cN & 3) == 0) {
+        const int lpr = cN >> 2;           // 16-byte chunks per row (<= 16 for N <= 64)
         const int rpp = 32 / lpr;          // rows per warp pass
         const int rr = lane / lpr, c4 = (lane - rr * lpr) * 4;
         const float4 dk = *reinterpret_cast<const float4*>(dst + c4);
         if (rr < rpp) {
-          for (int hh = rr; hh < N; hh += rpp) {
-            const float4 w4 = *reinterpret_cast<const float4*>(Wt + hh * N + c4);
+          const float* wsrc = Wt + rr * cN + c4;
+          float* adst = At + static_cast<size_t>(rr) * cN + c4;
+          const int stride = rpp * cN;
+          int hh = rr;
+          for (; hh + 3 * rpp < cN; hh += 4 * rpp) {
+            float4 w4[4];
+            float dh[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              w4[u] = *reinterpret_cast<const float4*>(wsrc + u * stride);
+              dh[u] = dst[hh + u * rpp];
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              float4 o;
+              o.x = fmaf(-(w4[u].x * dh[u]), dk.x, 0.f);
+              o.y = fmaf(-(w4[u].y * dh[u]), dk.y, 0.f);
+              o.z = fmaf(-(w4[u].z * dh[u]), dk.z, 0.f);
+              o.w = fmaf(-(w4[u].w * dh[u]), dk.w, 0.f);
+              *reinterpret_cast<float4*>(adst + u * stride) = o;
+            }
+            wsrc += 4 * stride;
+            adst += 4 * stride;
+          }
+          for (; hh < cN; hh += rpp) {
+            const float4 w4 = *reinterpret_cast<const float4*>(wsrc);
             const float dh = dst[hh];
             float4 o;
             o.x = fmaf(-(w4.x * dh), dk.x, 0.f);
             o.y = fmaf(-(w4.y * dh), dk.y, 0.f);
             o.z = fmaf(-(w4.z * dh), dk.z, 0.f);
             o.w = fmaf(-(w4.w * dh), dk.w, 0.f);
-            *reinterpret_cast<float4*>(At + static_cast<size_t>(hh) * N + c4) = o;
+            *reinterpret_cast<float4*>(adst) = o;
+            wsrc += stride;
+            adst += stride;
           }
         }
       } else {
         float dk[NJ];
 #pragma unroll
-        for (int j = 0; j < NJ; ++j) dk[j] = (lane + 32 * j < N) ? dst[lane + 32 * j] : 0.f;
-        for (int hh = 0; hh < N; ++hh) {
+        for (int j = 0; j < NJ; ++j) dk[j] = kv[j] ? dst[lane + 32 * j] : 0.f;
+        for (int hh = 0; hh < cN; ++hh) {
           const float dh = dst[hh];
 #pragma unroll
           for (int j = 0; j < NJ; ++j) {
             const int k = lane + 32 * j;
-            if (k < N) At[static_cast<size_t>(hh) * N + k] = fmaf(-(Wt[hh * N + k] * dh), dk[j], 0.f);
+            if (kv[j]) At[static_cast<size_t>(hh) * cN + k] = fmaf(-(Wt[hh * cN + k] * dh), dk[j], 0.f);
           }
         }
       }
@@ -325,7 +374,7 @@ int launch_fast(const float* rel, const int32_t* seg_off, const int64_t* a_off, 
   int per_sm = 1;
   SSTG_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, F_THREADS, smem), "occupancy");
   if (per_sm < 1) per_sm = 1;
-  const long long items = static_cast<long long>(S) * ((T + F_WARPS - 1) / F_WARPS);
+  const long long items = static_cast<long long>(S) * (T / F_WARPS);
   const long long want = static_cast<long long>(sms) * per_sm;
   const int grid = static_cast<int>(items < want ? items : want);
   kern<<<grid, F_THREADS, smem, st>>>(rel, seg_off, a_off, S, T, NP, wtile, V, A);
@@ -371,7 +420,7 @@ int launch_graph_build(const float* rel, const int32_t* seg_off, const int64_t* 
                        float* V, float* A, int flags, cudaStream_t st) {
   if (S == 0) return SSTG_OK;
   if (flags & SSTG_GRAPH_FP64) return launch_f<true>(rel, seg_off, a_off, S, T, max_n, V, A, flags, st);
-  if ((flags & SSTG_GRAPH_NORM_LAP) && !(flags & SSTG_GRAPH_V_ONLY) && max_n <= 64) {
+  if ((flags & SSTG_GRAPH_NORM_LAP) && !(flags & SSTG_GRAPH_V_ONLY) && max_n <= 64 && (T & 3) == 0) {
     if (max_n <= 32) return launch_fast<1>(rel, seg_off, a_off, S, T, max_n, V, A, st);
     return launch_fast<2>(rel, seg_off, a_off, S, T, max_n, V, A, st);
   }

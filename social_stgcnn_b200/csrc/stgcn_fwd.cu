@@ -31,7 +31,7 @@ namespace {
 
 constexpr int S_WARPS = T_OBS;  // one warp per observed timestep
 constexpr int S_THREADS = S_WARPS * 32;
-constexpr int S_STAGES = 4;
+constexpr int S_MAX_STAGES = 4;
 constexpr int S_PAD = 8;  // floats of slack per stage for the aligned-superset copies
 
 struct FoldedParams {
@@ -49,24 +49,24 @@ struct SmemLayout {
   size_t off_bar, off_g, off_p, off_ring, total;
 };
 
-__host__ __device__ inline SmemLayout make_layout(int max_n, size_t budget) {
+__host__ __device__ inline SmemLayout make_layout(int max_n, size_t budget, int stages) {
   SmemLayout L;
   L.NP = (max_n + 3) & ~3;
   size_t o = (sizeof(FoldedParams) + 15) & ~size_t(15);
   L.off_bar = o;
-  o += sizeof(uint64_t) * S_WARPS * S_STAGES;
+  o += sizeof(uint64_t) * S_WARPS * S_MAX_STAGES;
   L.off_g = o;
   o += sizeof(float) * S_WARPS * L.NP * 8;
   L.off_p = o;
   L.p_bufs = (L.NP <= 128) ? 2 : 1;
   o += sizeof(float) * L.p_bufs * C * T_OBS * L.NP;
   L.off_ring = o;
-  size_t per_stage = (budget - o) / (S_WARPS * S_STAGES) / sizeof(float);
+  size_t per_stage = (budget - o) / (S_WARPS * stages) / sizeof(float);
   per_stage &= ~size_t(3);
   long cf = static_cast<long>(per_stage) - S_PAD;
-  if (cf > 2048) cf = 2048;  // 8 KB copies are plenty
+  if (cf > 4096) cf = 4096;  // 16 KB copies are plenty
   L.chunk_floats = static_cast<int>(cf);
-  L.total = o + sizeof(float) * S_WARPS * S_STAGES * (L.chunk_floats + S_PAD);
+  L.total = o + sizeof(float) * S_WARPS * stages * (L.chunk_floats + S_PAD);
   return L;
 }
 
@@ -98,17 +98,17 @@ __device__ __forceinline__ void cursor_open(Cursor& c, int s, int S, int t, int 
 
 // CPS = CTAs per SM the kernel is compiled for (register cap 255 / 128): two co-resident CTAs
 // (16 warps) hide the shared-memory and mbarrier latencies of each other's math phases.
-template <int NJ, int CPS>
+template <int NJ, int CPS, int S_STAGES>
 __global__ void __launch_bounds__(S_THREADS, CPS)
 stgcn_fwd_kernel(const float* __restrict__ V, const float* __restrict__ A, const int32_t* __restrict__ seg_off,
                  const int64_t* __restrict__ a_off, int S, int max_n, const float* __restrict__ params,
                  const float* __restrict__ bn, float* __restrict__ H, int smem_budget) {
   extern __shared__ __align__(128) unsigned char smem[];
-  const SmemLayout L = make_layout(max_n, static_cast<size_t>(smem_budget));
+  const SmemLayout L = make_layout(max_n, static_cast<size_t>(smem_budget), S_STAGES);
   FoldedParams& fp = *reinterpret_cast<FoldedParams*>(smem);
   const int tid = threadIdx.x, lane = tid & 31, t = tid >> 5;
   const int NP = L.NP;
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + L.off_bar) + t * S_STAGES;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + L.off_bar) + t * S_MAX_STAGES;
   float* gbuf = reinterpret_cast<float*>(smem + L.off_g) + static_cast<size_t>(t) * NP * 8;  // [v][8]
   float* pbuf = reinterpret_cast<float*>(smem + L.off_p);                                    // [buf][c][t][NP]
   const int stage_floats = L.chunk_floats + S_PAD;
@@ -291,7 +291,7 @@ stgcn_fwd_kernel(const float* __restrict__ V, const float* __restrict__ A, const
   }
 }
 
-template <int NJ, int CPS>
+template <int NJ, int CPS, int STAGES>
 int launch_nj(const float* V, const float* A, const int32_t* seg_off, const int64_t* a_off, int S, int max_n,
               const float* params, const float* bn, float* H, int sm_count, cudaStream_t st) {
   int dev = 0, sms = 148, max_optin = 0;
@@ -300,9 +300,9 @@ int launch_nj(const float* V, const float* A, const int32_t* seg_off, const int6
   SSTG_CUDA_TRY(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev), "smem optin");
   // 227 KB for one CTA per SM; two CTAs share the SM's 228 KB (1 KB reserved per CTA)
   const int budget = CPS == 1 ? max_optin : (max_optin + 1024) / 2 - 1024;
-  const SmemLayout L = make_layout(max_n, static_cast<size_t>(budget));
+  const SmemLayout L = make_layout(max_n, static_cast<size_t>(budget), STAGES);
   if (L.chunk_floats < L.NP) return SSTG_ETOOBIG;
-  auto kern = stgcn_fwd_kernel<NJ, CPS>;
+  auto kern = stgcn_fwd_kernel<NJ, CPS, STAGES>;
   SSTG_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(L.total)),
                 "stgcn smem attr");
   if (sm_count > 0 && sm_count < sms) sms = sm_count;
@@ -314,6 +314,13 @@ int launch_nj(const float* V, const float* A, const int32_t* seg_off, const int6
 }
 
 // SSTG_STGCN_CPS=1|2 overrides the CTAs-per-SM choice (tuning knob; default 2 for N <= 64).
+// SSTG_STGCN_STAGES=2|3|4: ring depth per warp when two CTAs share an SM (tuning knob; default 2:
+// measured 5.40 TB/s vs 4.92 (3) and 4.73 (4) at N = 64 -- fewer, larger bulk copies per slice).
+int stgcn_stages_default() {
+  const char* e = getenv("SSTG_STGCN_STAGES");
+  if (e && e[0] >= '2' && e[0] <= '4') return e[0] - '0';
+  return 2;
+}
 int stgcn_cps_default(int max_n) {
   const char* e = getenv("SSTG_STGCN_CPS");
   if (e && (e[0] == '1' || e[0] == '2')) return e[0] - '0';
@@ -327,14 +334,21 @@ int launch_stgcn_forward(const float* V, const float* A, const int32_t* seg_off,
                          cudaStream_t st) {
   if (S == 0) return SSTG_OK;
   const bool two = stgcn_cps_default(max_n) == 2 && max_n <= 64;
-  if (max_n <= 32)
-    return two ? launch_nj<1, 2>(V, A, seg_off, a_off, S, max_n, params, bn, H, sm_count, st)
-               : launch_nj<1, 1>(V, A, seg_off, a_off, S, max_n, params, bn, H, sm_count, st);
-  if (max_n <= 64)
-    return two ? launch_nj<2, 2>(V, A, seg_off, a_off, S, max_n, params, bn, H, sm_count, st)
-               : launch_nj<2, 1>(V, A, seg_off, a_off, S, max_n, params, bn, H, sm_count, st);
-  if (max_n <= 128) return launch_nj<4, 1>(V, A, seg_off, a_off, S, max_n, params, bn, H, sm_count, st);
-  return launch_nj<8, 1>(V, A, seg_off, a_off, S, max_n, params, bn, H, sm_count, st);
+  const int stages = stgcn_stages_default();
+#define SSTG_ARGS V, A, seg_off, a_off, S, max_n, params, bn, H, sm_count, st
+  if (max_n <= 32) {
+    if (!two) return launch_nj<1, 1, 4>(SSTG_ARGS);
+    return stages == 2 ? launch_nj<1, 2, 2>(SSTG_ARGS) : stages == 3 ? launch_nj<1, 2, 3>(SSTG_ARGS)
+                                                                     : launch_nj<1, 2, 4>(SSTG_ARGS);
+  }
+  if (max_n <= 64) {
+    if (!two) return launch_nj<2, 1, 4>(SSTG_ARGS);
+    return stages == 2 ? launch_nj<2, 2, 2>(SSTG_ARGS) : stages == 3 ? launch_nj<2, 2, 3>(SSTG_ARGS)
+                                                                     : launch_nj<2, 2, 4>(SSTG_ARGS);
+  }
+  if (max_n <= 128) return launch_nj<4, 1, 4>(SSTG_ARGS);
+  return launch_nj<8, 1, 4>(SSTG_ARGS);
+#undef SSTG_ARGS
 }
 
 }  // namespace sstg

@@ -287,8 +287,8 @@ class InferenceEngine:
                 "in": [{"obs": torch.empty(mp, 2, L.T_OBS, dtype=f, device=dev),
                         "pred": torch.empty(mp, 2, L.T_PRED, dtype=f, device=dev),
                         "last": torch.empty(mp, 2, dtype=f, device=dev)} for _ in range(2)],
-                "d_out": torch.empty(2, plan.P, dtype=torch.float64, device=dev),
-                "h_out": torch.empty(2, plan.P, dtype=torch.float64).pin_memory(),
+                "d_out": [torch.empty(plan.P, dtype=torch.float64, device=dev) for _ in range(2)],
+                "h_out": [torch.empty(plan.P, dtype=torch.float64).pin_memory() for _ in range(2)],
                 "s_h2d": torch.cuda.Stream(dev), "s_d2h": torch.cuda.Stream(dev),
                 "free": [torch.cuda.Event() for _ in range(2)],
             }
@@ -310,11 +310,13 @@ class InferenceEngine:
                 ready.record(s_h2d)
             main.wait_event(ready)
             self.infer(sub, b["obs"][:n], b["pred"][:n], b["last"][:n], K, seed=seed + 0x9E3779B1 * i,
-                       min_ade=st["d_out"][0, p_lo:p_hi], min_fde=st["d_out"][1, p_lo:p_hi], **kw)
+                       min_ade=st["d_out"][0][p_lo:p_hi], min_fde=st["d_out"][1][p_lo:p_hi], **kw)
             st["free"][i & 1].record(main)
             s_d2h.wait_event(st["free"][i & 1])
             with torch.cuda.stream(s_d2h):
-                st["h_out"][:, p_lo:p_hi].copy_(st["d_out"][:, p_lo:p_hi], non_blocking=True)
+                # contiguous 1-D slices: a strided D2H copy would go through a pageable staging buffer and block
+                st["h_out"][0][p_lo:p_hi].copy_(st["d_out"][0][p_lo:p_hi], non_blocking=True)
+                st["h_out"][1][p_lo:p_hi].copy_(st["d_out"][1][p_lo:p_hi], non_blocking=True)
         main.wait_stream(s_d2h)
         main.synchronize()
         return st["h_out"][0].numpy(), st["h_out"][1].numpy()
