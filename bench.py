@@ -97,6 +97,16 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(self.reasons), "samples": len(self.sm)}
 
 
+def profiled_traffic():
+    """DRAM bytes of the st_gcn kernel from the committed ncu --set full capture (profiles/traffic.json:
+    dram__bytes_read.sum + dram__bytes_write.sum for one launch of `scenes` scenes), or None."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        return json.load(open(p))["stgcn_fwd_kernel"]
+    except Exception:
+        return None
+
+
 def measured_peak_gbs():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -182,6 +192,64 @@ def run_reference(args):
 
 
 # ---------------------------------------------------------------------------------
+# training leg (BASELINE.json config 2): optimiser groups of 128 ragged scenes
+# ---------------------------------------------------------------------------------
+def synth_ragged_counts(num_scenes, seed):
+    """Pedestrian counts shaped like the ETH/UCY train splits (median 4-6,
+    mean ~11, p95 ~36, max 57): log-normal, clipped to [2, 57]."""
+    rng = np.random.default_rng(seed)
+    n = np.rint(np.exp(rng.normal(1.8, 0.9, num_scenes))).astype(np.int32)
+    return np.clip(n, 2, 57)
+
+
+def run_train_leg(dev, world, rank, steps, warmup, batch=128):
+    """scenes/s of train() (graph build + train-mode forward + NLL + backward + BN stats + SGD)
+    on packed groups of `batch` scenes; with world > 1 every group is sharded over the ranks and
+    the 7,563-float gradient is all-reduced over NCCL.  Device timing, max over ranks."""
+    import torch
+    import torch.distributed as dist
+    import social_stgcnn_b200 as sstg
+    from social_stgcnn_b200 import parallel as Pl
+    params, bn = load_weights()
+    eng = sstg.TrainEngine(params, bn, dev)
+    trainer = Pl.DistributedTrainer(eng) if world > 1 else None
+    groups = []
+    for g in range(8):                                    # 8 distinct groups, cycled
+        n = synth_ragged_counts(batch, 100 + g)
+        obs, pred, _ = synth_batch(int(n.sum()), 1, 7000 + g)
+        groups.append((n, sstg.ScenePlan(n), obs.to(dev), pred.to(dev)))
+
+    def one(i):
+        n, plan, obs, pred = groups[i % len(groups)]
+        if trainer is not None:
+            trainer.step(n, obs, pred, batch, 1e-4)
+        else:
+            eng.step(plan, obs, pred, batch, 1e-4)
+
+    for i in range(warmup):
+        one(i)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        one(i)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms[0])
+    peds = float(np.mean([g[0].sum() for g in groups]))
+    return {"value": batch * steps / (ms * 1e-3), "unit": "scenes/s", "ms_per_group": ms / steps, "batch": batch,
+            "groups_timed": steps, "mean_peds_per_group": peds, "n_gpus": world,
+            "what": "train(): graph build + train-mode fwd (per-scene BN stats) + NLL + full bwd + BN running stats "
+                    "+ SGD, one packed ragged group of 128 ETH/UCY-shaped scenes per step"
+                    + ("; group sharded over ranks, NCCL all-reduce of the 7,563-float gradient" if world > 1 else "")}
+
+
+# ---------------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------------
 def run_ours(args):
@@ -253,15 +321,28 @@ def run_ours(args):
 
     # ---- e2e: host buffers -> H2D -> pipeline -> D2H, through the public API
     for _ in range(max(1, min(2, args.warmup))):
-        eng.infer_host(plan, obs_h, pred_h, last_h, K_SAMPLES, seed=args.seed)
+        eng.infer_host(plan, obs_h, pred_h, last_h, K_SAMPLES, seed=args.seed, chunk_scenes=args.chunk_scenes)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
-        a_h, f_h = eng.infer_host(plan, obs_h, pred_h, last_h, K_SAMPLES, seed=args.seed)
+        a_h, f_h = eng.infer_host(plan, obs_h, pred_h, last_h, K_SAMPLES, seed=args.seed,
+                                  chunk_scenes=args.chunk_scenes)
     e1.record()
     barrier()
     ms_e2e = e0.elapsed_time(e1)
+
+    # ---- H2D copy bandwidth of this box (context for e2e: PCIe carries 168 B per pedestrian)
+    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    c0.record()
+    obs.copy_(obs_h, non_blocking=True)
+    pred.copy_(pred_h, non_blocking=True)
+    c1.record()
+    torch.cuda.synchronize()
+    h2d_gbs = (obs_h.numel() + pred_h.numel()) * 4 / (c0.elapsed_time(c1) * 1e-3) / 1e9
+    train = None
+    if not args.no_train:
+        train = run_train_leg(dev, world, rank, steps=max(20, 10 * args.steps), warmup=5)
 
     t = torch.tensor([ms_total, ms_e2e], dtype=torch.float64, device=dev)
     red = torch.tensor([sum_a, sum_f, float(plan.P)], dtype=torch.float64, device=dev)
@@ -294,12 +375,20 @@ def run_ours(args):
                        "l2_policy": "inputs larger than L2 (A is %.1f GB per step)" % (plan.a_floats * 4 / 1e9),
                        "parallelism": f"scene-sharded x{world}, no data-path collective"},
             "roofline": {"kernel": "stgcn_fwd_kernel", "bound": "hbm", "achieved": achieved, "peak": peak,
-                         "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": (tr["dram_bytes"] * S / tr["scenes"] if (tr := profiled_traffic()) else None),
+                         "traffic_source": (f"ncu --set full, {tr['file']}: {tr['dram_bytes']} B for a launch of "
+                                            f"{tr['scenes']} scenes, scaled to this launch" if tr else None),
+                         "algorithmic_bytes_per_launch": bytes_s, "peak_source": peak_src,
                          "share_of_step": kern_ms["stgcn_forward"] / ksum},
             "kernels": kernels,
             "e2e": {"value": S * world * args.steps / (ms_e2e * 1e-3), "unit": UNIT,
-                    "h2d_bytes_per_step": eng.h2d_bytes(plan), "d2h_bytes_per_step": eng.d2h_bytes(plan)},
+                    "h2d_bytes_per_step": eng.h2d_bytes(plan), "d2h_bytes_per_step": eng.d2h_bytes(plan),
+                    "ms_per_step": ms_e2e / args.steps, "h2d_GBps_measured": round(h2d_gbs, 1),
+                    "how": f"InferenceEngine.infer_host: pinned host buffers, {len(plan.chunks(args.chunk_scenes))} chunks of "
+                           f"{args.chunk_scenes} scenes software-pipelined over 3 streams (H2D | kernels | D2H)"},
             "gpu_launches": 5 * args.steps,
+            "train": train,
             "clocks": sampler.result(),
             "result": {"ade": red[0].item() / red[2].item(), "fde": red[1].item() / red[2].item(),
                        "peds": int(red[2].item())},
@@ -330,6 +419,8 @@ def main():
     ap.add_argument("--scenes-per-gpu", type=int, default=131072)
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train", action="store_true", help="skip the training-throughput leg")
+    ap.add_argument("--chunk-scenes", type=int, default=16384, help="scenes per pipeline chunk of the e2e path")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
