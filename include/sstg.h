@@ -191,6 +191,22 @@ int sstg_backward(const float* V, const float* A, const int32_t* seg_off, const 
 int sstg_sgd_step(float* params, const float* grad, int32_t n, float lr, float clip_norm,
                   float* grad_norm_out, void* stream);
 
+/* ---- one optimiser group of train() in ONE call (train.py:38-74 for `batch_size` scenes) --------
+ * graph build (obs: V + A; pred: V only) -> sstg_forward_train -> sstg_nll_backward ->
+ * sstg_backward -> sstg_bn_running_update -> [sstg_sgd_step if lr != 0], all on `stream`.
+ *   obs_rel [P,2,8], pred_rel [P,2,12]     TrajectoryDataset.obs_traj_rel / pred_traj_rel rows of the group
+ *   params [7563], bn [30]                 updated in place
+ *   scene_weight [S]                       1/batch_size, 0 for the unscored last scene (may be NULL = 1)
+ *   ws                                     caller-owned scratch of >= sstg_train_step_workspace() floats, 16-byte aligned
+ *   loss [S] per-scene NLL, grad [7563], group_loss [1] = sum_s weight[s]*loss[s] (may be NULL)
+ *   graph_flags                            SSTG_GRAPH_FP64 or 0 (NORM_LAP is implied) */
+int64_t sstg_train_step_workspace(int32_t S, int32_t n_tiles, int32_t total_peds, int64_t a_floats);
+int sstg_train_step(const float* obs_rel, const float* pred_rel, const int32_t* seg_off, const int64_t* a_off,
+                    const int32_t* tile_off, int32_t S, int32_t n_tiles, int32_t max_n, int32_t total_peds,
+                    int64_t a_floats, float* params, float* bn, const float* scene_weight, float* ws,
+                    int64_t ws_floats, float lr, float clip_norm, double bn_momentum, int32_t graph_flags,
+                    float* loss, float* grad, float* group_loss, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -41,6 +41,9 @@ _SIGS.update({
     "sstg_backward": (C.c_int, [_p, _p, _p, _p, _p, _i32, _i32, _i32, _i32, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
     "sstg_rel_to_abs": (C.c_int, [_p, _p, _p, _i32, _i32, _i32, _p, _p]),
     "sstg_traj_error": (C.c_int, [_p, _p, _p, _i32, _i32, _i32, _p, _p, _p]),
+    "sstg_train_step_workspace": (C.c_int64, [_i32, _i32, _i32, _i64]),
+    "sstg_train_step": (C.c_int, [_p, _p, _p, _p, _p, _i32, _i32, _i32, _i32, _i64, _p, _p, _p, _p, _i64, _f32, _f32,
+                                  _f64, _i32, _p, _p, _p, _p]),
     "sstg_sgd_step": (C.c_int, [_p, _p, _i32, _f32, _f32, _p, _p]),
 })
 

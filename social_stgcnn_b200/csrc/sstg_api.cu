@@ -224,4 +224,68 @@ int sstg_sgd_step(float* params, const float* grad, int32_t n, float lr, float c
   return launch_sgd_step(params, grad, n, lr, clip_norm, grad_norm_out, static_cast<cudaStream_t>(stream));
 }
 
+namespace {
+struct TrainWs {
+  int64_t V, A, Vtr, save, stats, vp, dvp, dH, pst, ptx, total;
+};
+inline int64_t up4(int64_t x) { return (x + 3) & ~int64_t(3); }
+TrainWs train_ws_layout(int32_t S, int32_t n_tiles, int32_t P, int64_t a_floats) {
+  TrainWs w;
+  int64_t o = 0;
+  w.V = o;      o += up4(int64_t(P) * 16);
+  w.A = o;      o += up4(a_floats);
+  w.Vtr = o;    o += up4(int64_t(P) * 24);
+  w.save = o;   o += up4(int64_t(P) * SSTG_SAVE_FLOATS_PER_PED);
+  w.stats = o;  o += up4(int64_t(S) * SSTG_N_BN);
+  w.vp = o;     o += up4(int64_t(P) * 60);
+  w.dvp = o;    o += up4(int64_t(P) * 60);
+  w.dH = o;     o += up4(int64_t(P) * 40);
+  w.pst = o;    o += up4(int64_t(stgcn_train_bwd_rows(S)) * SSTG_ST_PARAMS);
+  w.ptx = o;    o += up4(int64_t(txpcnn_bwd_rows(n_tiles)) * SSTG_TXP_GRAD_STRIDE);
+  w.total = o;
+  return w;
+}
+}  // namespace
+
+int64_t sstg_train_step_workspace(int32_t S, int32_t n_tiles, int32_t total_peds, int64_t a_floats) {
+  if (S < 0 || n_tiles < 0 || total_peds < 0 || a_floats < 0) return SSTG_EINVAL;
+  return train_ws_layout(S, n_tiles, total_peds, a_floats).total;
+}
+
+int sstg_train_step(const float* obs_rel, const float* pred_rel, const int32_t* seg_off, const int64_t* a_off,
+                    const int32_t* tile_off, int32_t S, int32_t n_tiles, int32_t max_n, int32_t total_peds,
+                    int64_t a_floats, float* params, float* bn, const float* scene_weight, float* ws,
+                    int64_t ws_floats, float lr, float clip_norm, double bn_momentum, int32_t graph_flags,
+                    float* loss, float* grad, float* group_loss, void* stream) {
+  if (S < 0 || n_tiles < 0 || max_n < 1 || total_peds < 0 || a_floats < 0) return SSTG_EINVAL;
+  if (max_n > SSTG_MAX_PEDS) return SSTG_ETOOBIG;
+  if (!params || !bn || !grad || !loss) return SSTG_EINVAL;
+  if (S == 0) return sstg_backward(nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0, 1, 0, nullptr, nullptr, nullptr,
+                                   nullptr, nullptr, nullptr, nullptr, grad, stream);
+  if (!obs_rel || !pred_rel || !seg_off || !a_off || !tile_off || !ws || !aligned16(ws)) return SSTG_EINVAL;
+  const TrainWs w = train_ws_layout(S, n_tiles, total_peds, a_floats);
+  if (ws_floats < w.total) return SSTG_EINVAL;
+  const int gf = SSTG_GRAPH_NORM_LAP | (graph_flags & SSTG_GRAPH_FP64);
+  int rc = sstg_graph_build(obs_rel, seg_off, a_off, S, SSTG_T_OBS, max_n, ws + w.V, ws + w.A, gf, stream);
+  if (rc) return rc;
+  rc = sstg_graph_build(pred_rel, seg_off, nullptr, S, SSTG_T_PRED, max_n, ws + w.Vtr, nullptr, SSTG_GRAPH_V_ONLY, stream);
+  if (rc) return rc;
+  rc = sstg_forward_train(ws + w.V, ws + w.A, seg_off, a_off, tile_off, S, n_tiles, max_n, total_peds, params,
+                          ws + w.save, ws + w.stats, ws + w.vp, stream);
+  if (rc) return rc;
+  rc = sstg_nll_backward(ws + w.vp, ws + w.Vtr, seg_off, S, scene_weight, loss, ws + w.dvp, stream);
+  if (rc) return rc;
+  rc = sstg_backward(ws + w.V, ws + w.A, seg_off, a_off, tile_off, S, n_tiles, max_n, total_peds, params, ws + w.save,
+                     ws + w.stats, ws + w.dvp, ws + w.dH, ws + w.pst, ws + w.ptx, grad, stream);
+  if (rc) return rc;
+  rc = sstg_bn_running_update(ws + w.stats, seg_off, S, bn_momentum, bn, stream);
+  if (rc) return rc;
+  if (group_loss) {
+    rc = launch_group_loss(loss, scene_weight, S, group_loss, static_cast<cudaStream_t>(stream));
+    if (rc) return rc;
+  }
+  if (lr != 0.f) rc = sstg_sgd_step(params, grad, SSTG_N_PARAMS, lr, clip_norm, nullptr, stream);
+  return rc;
+}
+
 }  // extern "C"

@@ -640,6 +640,16 @@ sgd_step_kernel(float* __restrict__ params, const float* __restrict__ grad, int 
   for (int i = threadIdx.x; i < n; i += blockDim.x) params[i] = fmaf(-step, grad[i], params[i]);
 }
 
+// group loss = sum_s weight[s] * loss[s] (train.py:58-66), fixed order, fp64 accumulate
+__global__ void group_loss_kernel(const float* __restrict__ loss, const float* __restrict__ weight, int S,
+                                  float* __restrict__ out) {
+  double acc = 0.0;
+  for (int s = threadIdx.x; s < S; s += 32) acc += static_cast<double>(loss[s]) * (weight ? weight[s] : 1.f);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (threadIdx.x == 0) *out = static_cast<float>(acc);
+}
+
 size_t train_fwd_smem(int NP) {
   return ((sizeof(TrainParams) + 15) & ~size_t(15)) + sizeof(float) * (R_WARPS * 10 + R_WARPS * NP * 8 + C * T_OBS * NP);
 }
@@ -721,6 +731,12 @@ int launch_grad_finalize(const float* part_st, int rows_st, const float* part_tx
   grad_finalize_kernel<<<(SSTG_N_PARAMS + 255) / 256, 256, 0, st>>>(part_st, rows_st, part_tx, rows_tx, tx_stride,
                                                                    grad);
   SSTG_CUDA_TRY(cudaGetLastError(), "grad_finalize launch");
+  return SSTG_OK;
+}
+
+int launch_group_loss(const float* loss, const float* weight, int S, float* out, cudaStream_t st) {
+  group_loss_kernel<<<1, 32, 0, st>>>(loss, weight, S, out);
+  SSTG_CUDA_TRY(cudaGetLastError(), "group_loss launch");
   return SSTG_OK;
 }
 

@@ -84,11 +84,18 @@ class ScenePlan:
         if device.index is None:
             device = torch.device("cuda", torch.cuda.current_device())
         if device not in self._dev:
+            # one host->device copy for the three offset tables: [a_off int64 | seg_off int32 | tile_off int32]
+            nb_a, nb_s, nb_t = self.a_off.nbytes, self.seg_off.nbytes, self.tile_off.nbytes
+            host = np.empty(nb_a + nb_s + nb_t, np.uint8)
+            host[:nb_a] = self.a_off.view(np.uint8)
+            host[nb_a:nb_a + nb_s] = self.seg_off.view(np.uint8)
+            host[nb_a + nb_s:] = self.tile_off.view(np.uint8)
+            buf = torch.from_numpy(host).to(device)
             self._dev[device] = DevicePlan(
                 self, device,
-                torch.from_numpy(self.seg_off).to(device),
-                torch.from_numpy(self.a_off).to(device),
-                torch.from_numpy(self.tile_off).to(device))
+                buf[nb_a:nb_a + nb_s].view(torch.int32),
+                buf[:nb_a].view(torch.int64),
+                buf[nb_a + nb_s:].view(torch.int32))
         return self._dev[device]
 
 
@@ -473,7 +480,47 @@ class TrainEngine:
         backward(dp, V, A, self.params, save, stats, dvp, grad=self.grad, ws=self._ws)
         return {"loss": loss, "grad": self.grad, "scene_stats": stats, "V_pred": vp, "weight": w}
 
+    def _step_buffers(self, plan: ScenePlan, batch_size: int):
+        """Grow-only scratch of sstg_train_step, per-scene loss, and the cached loss weights."""
+        lib = L.load()
+        need = int(lib.sstg_train_step_workspace(plan.S, plan.n_tiles, plan.P, plan.a_floats))
+        if need < 0:
+            L.check(need, "sstg_train_step_workspace")
+        ws = self._ws.get("step")
+        if ws is None or ws.numel() < need:
+            self._ws["step"] = None
+            ws = self._ws["step"] = torch.empty(max(need, 4), dtype=torch.float32, device=self.device)
+        loss = self._ws.get("loss")
+        if loss is None or loss.numel() < plan.S + 1:
+            loss = self._ws["loss"] = torch.empty(max(plan.S + 1, 129), dtype=torch.float32, device=self.device)
+        wkey = ("w", plan.S, batch_size)
+        w = self._ws.get(wkey)
+        if w is None:
+            w = self._ws[wkey] = torch.from_numpy(group_weights(plan.S, batch_size)).to(self.device)
+        return ws, need, loss, w
+
     def step(self, plan: ScenePlan, obs_rel, pred_rel, batch_size: int, lr: float, clip_grad=None,
+             *, graph_fp64: bool = True):
+        """One optimiser group in ONE library call (sstg_train_step): returns the group loss
+        (sum_i w_i * l_i) as a 0-dim device tensor (valid until the next step)."""
+        dev = self.device
+        dp = plan.on(dev)
+        _need(obs_rel, torch.float32, "obs_rel", dev)
+        _need(pred_rel, torch.float32, "pred_rel", dev)
+        if tuple(obs_rel.shape) != (plan.P, 2, L.T_OBS) or tuple(pred_rel.shape) != (plan.P, 2, L.T_PRED):
+            raise ValueError(f"obs_rel / pred_rel must be [{plan.P}, 2, 8] / [{plan.P}, 2, 12]")
+        ws, need, loss, w = self._step_buffers(plan, batch_size)
+        with torch.cuda.device(dev):
+            L.check(L.load().sstg_train_step(
+                _ptr(obs_rel), _ptr(pred_rel), _ptr(dp.seg_off), _ptr(dp.a_off), _ptr(dp.tile_off), plan.S,
+                plan.n_tiles, plan.max_n, plan.P, plan.a_floats, _ptr(self.params), _ptr(self.bn), _ptr(w), _ptr(ws),
+                need, float(lr), float(clip_grad or 0.0), 0.1, L.GRAPH_FP64 if graph_fp64 else 0,
+                _ptr(loss), _ptr(self.grad), loss.data_ptr() + 4 * plan.S, _stream(dev)), "sstg_train_step")
+        self.num_batches_tracked += plan.S
+        self.last_loss = loss[:plan.S]
+        return loss[plan.S]
+
+    def step_unfused(self, plan: ScenePlan, obs_rel, pred_rel, batch_size: int, lr: float, clip_grad=None,
              *, graph_fp64: bool = True):
         """One optimiser group: returns the group loss (sum_i w_i * l_i) as a 0-dim device tensor."""
         r = self.forward_backward(plan, obs_rel, pred_rel, group_weights(plan.S, batch_size), graph_fp64=graph_fp64)

@@ -220,3 +220,23 @@ def test_backward_is_deterministic_and_sgd(golden, dev):
     loss = eng.step(plan, o, p, batch_size=8, lr=0.01)
     assert np.isfinite(float(loss)) and eng.num_batches_tracked == 8
     assert not torch.equal(eng.params, w0)
+
+
+def test_fused_step_call_equals_separate_calls(golden, dev):
+    """sstg_train_step (one library call per optimiser group) == the same group issued call by
+    call through the functional ops: identical weights, BN buffers, loss, bit for bit."""
+    import social_stgcnn_b200 as sstg
+    from oracle import stgcnn_oracle as O
+    n_list = [5, 3, 64, 2, 17, 31, 4, 9, 2, 2, 57, 6]
+    obs_rel, pred_rel, _ = O.synthetic_scenes(1, sum(n_list), seed=21)
+    params, bn = golden.params("hotel") if "hotel.params" in golden.weights.files else golden.params("eth")
+    o, p = torch.from_numpy(obs_rel).to(dev), torch.from_numpy(pred_rel).to(dev)
+    plan = sstg.ScenePlan(n_list)
+    a, b = sstg.TrainEngine(params, bn, dev), sstg.TrainEngine(params, bn, dev)
+    for it in range(3):
+        la = a.step(plan, o, p, batch_size=12, lr=0.01, clip_grad=10.0)
+        lb = b.step_unfused(plan, o, p, batch_size=12, lr=0.01, clip_grad=10.0)
+        torch.cuda.synchronize()
+        assert torch.equal(a.params, b.params) and torch.equal(a.bn, b.bn), it
+        assert abs(float(la) - float(lb)) < 1e-6 * max(1.0, abs(float(lb)))
+    assert a.num_batches_tracked == b.num_batches_tracked == 36
