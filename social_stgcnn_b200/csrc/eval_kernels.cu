@@ -84,7 +84,8 @@ __global__ void __launch_bounds__(E_THREADS, 2)
 sample_ade_fde_kernel(const float* __restrict__ Vpred, const float* __restrict__ Vtr,
                       const float* __restrict__ last_obs, const int32_t* __restrict__ seg_off, int S, int K,
                       const float* __restrict__ eps, uint64_t seed, float* __restrict__ eps_out,
-                      double* __restrict__ min_ade, double* __restrict__ min_fde, float* __restrict__ pred_abs) {
+                      double* __restrict__ min_ade, double* __restrict__ min_fde, float* __restrict__ pred_abs,
+                      int vtr_is_rel) {
   using Acc = typename std::conditional<EXACT, double, float>::type;
   // [t][field][ped]: mux, muy, L00, L10, L11, gtx, gty
   __shared__ float par[T_PRED][7][E_PEDS];
@@ -173,14 +174,30 @@ sample_ade_fde_kernel(const float* __restrict__ Vpred, const float* __restrict__
   // fp32 sum (double rounding through a 53 >= 2*24+2 bit format is innocuous), so __fadd_rn is bit-exact.
   if (tid < E_PEDS && sc_N[tid] > 0) {
     const int N = sc_N[tid], n0 = sc_n0[tid], nl = p_base + tid - n0;
-    const float2* vt = reinterpret_cast<const float2*>(Vtr) + static_cast<size_t>(n0) * T_PRED + nl;
     const float2 init = reinterpret_cast<const float2*>(last_obs)[p_base + tid];
+    float rx[T_PRED], ry[T_PRED];
+    if (vtr_is_rel) {  // Vtr is pred_traj_rel [P,2,12]: this pedestrian's 24 floats are contiguous
+      const float4* pr = reinterpret_cast<const float4*>(Vtr + static_cast<size_t>(p_base + tid) * (2 * T_PRED));
+#pragma unroll
+      for (int i = 0; i < T_PRED / 4; ++i) {
+        const float4 a = pr[i], b = pr[T_PRED / 4 + i];
+        rx[4 * i] = a.x, rx[4 * i + 1] = a.y, rx[4 * i + 2] = a.z, rx[4 * i + 3] = a.w;
+        ry[4 * i] = b.x, ry[4 * i + 1] = b.y, ry[4 * i + 2] = b.z, ry[4 * i + 3] = b.w;
+      }
+    } else {
+      const float2* vt = reinterpret_cast<const float2*>(Vtr) + static_cast<size_t>(n0) * T_PRED + nl;
+#pragma unroll
+      for (int t = 0; t < T_PRED; ++t) {
+        const float2 v = vt[t * N];
+        rx[t] = v.x;
+        ry[t] = v.y;
+      }
+    }
     float cx = 0.f, cy = 0.f;
 #pragma unroll
     for (int t = 0; t < T_PRED; ++t) {
-      const float2 v = vt[t * N];
-      cx = __fadd_rn(cx, v.x);
-      cy = __fadd_rn(cy, v.y);
+      cx = __fadd_rn(cx, rx[t]);
+      cy = __fadd_rn(cy, ry[t]);
       par[t][5][tid] = __fadd_rn(cx, init.x);
       par[t][6][tid] = __fadd_rn(cy, init.y);
     }
@@ -341,9 +358,10 @@ int launch_sample_ade_fde(const float* Vpred, const float* Vtr, const float* las
   const int grid = (P + E_PEDS - 1) / E_PEDS;
   const bool exact = flags & SSTG_EVAL_FP64_DIST, philox = eps == nullptr;
   const bool extra = eps_out != nullptr || pred_abs != nullptr;
+  const int rel_in = (flags & SSTG_EVAL_VTR_IS_REL) ? 1 : 0;
 #define SSTG_LAUNCH_SAMPLE(EX, PH, XT)                                                                         \
   sample_ade_fde_kernel<EX, PH, XT><<<grid, E_THREADS, 0, st>>>(Vpred, Vtr, last_obs, seg_off, S, K, eps, seed, \
-                                                                eps_out, min_ade, min_fde, pred_abs)
+                                                                eps_out, min_ade, min_fde, pred_abs, rel_in)
   if (exact) {
     if (philox) { if (extra) SSTG_LAUNCH_SAMPLE(true, true, true); else SSTG_LAUNCH_SAMPLE(true, true, false); }
     else        { if (extra) SSTG_LAUNCH_SAMPLE(true, false, true); else SSTG_LAUNCH_SAMPLE(true, false, false); }

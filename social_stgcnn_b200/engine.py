@@ -180,9 +180,10 @@ def nll_forward(dp: DevicePlan, Vpred, Vtr, *, loss=None):
 
 def sample_ade_fde(dp: DevicePlan, Vpred, Vtr, last_obs, K: int = 20, *, eps=None, seed: int = 0,
                    want_eps: bool = False, want_pred: bool = False, fp64_dist: bool = True,
-                   min_ade=None, min_fde=None):
+                   min_ade=None, min_fde=None, vtr_is_rel: bool = False):
     """test.py:59-123 for the packed batch.  Returns dict(min_ade[P] f64, min_fde[P] f64,
-    eps (noise used, if want_eps), pred_abs (K,12,N,2 blocks, if want_pred))."""
+    eps (noise used, if want_eps), pred_abs (K,12,N,2 blocks, if want_pred)).
+    vtr_is_rel: `Vtr` is pred_traj_rel [P,2,12] itself (saves building the V_tr blocks)."""
     h, dev = dp.host, dp.device
     for t, w in ((Vpred, "Vpred"), (Vtr, "Vtr"), (last_obs, "last_obs")):
         _need(t, torch.float32, w, dev)
@@ -202,7 +203,9 @@ def sample_ade_fde(dp: DevicePlan, Vpred, Vtr, last_obs, K: int = 20, *, eps=Non
     with torch.cuda.device(dev):
         L.check(L.load().sstg_sample_ade_fde(_ptr(Vpred), _ptr(Vtr), _ptr(last_obs), _ptr(dp.seg_off), h.S, h.P, K,
                                              _ptr(eps), seed & (2 ** 64 - 1), _ptr(eps_out), _ptr(min_ade),
-                                             _ptr(min_fde), _ptr(pred), L.EVAL_FP64_DIST if fp64_dist else 0,
+                                             _ptr(min_fde), _ptr(pred),
+                                             (L.EVAL_FP64_DIST if fp64_dist else 0) |
+                                             (L.EVAL_VTR_IS_REL if vtr_is_rel else 0),
                                              _stream(dev)), "sstg_sample_ade_fde")
     return {"min_ade": min_ade, "min_fde": min_fde, "eps": eps_out, "pred_abs": pred}
 
@@ -256,17 +259,18 @@ class InferenceEngine:
 
     def infer(self, plan: ScenePlan, obs_rel, pred_rel, last_obs, K: int = 20, *, eps=None, seed: int = 0,
               graph_fp64: bool = False, fp64_dist: bool = False, want_eps: bool = False, want_pred: bool = False,
-              min_ade=None, min_fde=None):
+              min_ade=None, min_fde=None, want_vtr: bool = True):
         """Device-resident inputs: obs_rel [P,2,8], pred_rel [P,2,12], last_obs [P,2].
         Returns the workspace dict (views valid until the next call) plus eps / pred_abs."""
         dp = plan.on(self.device)
         ws = self.workspace(plan)
         graph_build(dp, obs_rel, L.T_OBS, fp64=graph_fp64, V=ws["V_obs"], A=ws["A_obs"])
-        graph_build(dp, pred_rel, L.T_PRED, v_only=True, V=ws["V_tr"])
+        if want_vtr:  # the (12,N,2) target blocks (V_tr of the dataset tuple; needed by the NLL, not by ADE/FDE)
+            graph_build(dp, pred_rel, L.T_PRED, v_only=True, V=ws["V_tr"])
         stgcn_forward(dp, ws["V_obs"], ws["A_obs"], self.params, self.bn, H=ws["H"])
         txpcnn_forward(dp, ws["H"], self.params, out=ws["V_pred"])
-        r = sample_ade_fde(dp, ws["V_pred"], ws["V_tr"], last_obs, K, eps=eps, seed=seed, want_eps=want_eps,
-                           want_pred=want_pred, fp64_dist=fp64_dist,
+        r = sample_ade_fde(dp, ws["V_pred"], ws["V_tr"] if want_vtr else pred_rel, last_obs, K, eps=eps, seed=seed,
+                           want_eps=want_eps, want_pred=want_pred, fp64_dist=fp64_dist, vtr_is_rel=not want_vtr,
                            min_ade=ws["min_ade"] if min_ade is None else min_ade,
                            min_fde=ws["min_fde"] if min_fde is None else min_fde)
         out = dict(ws)
@@ -274,7 +278,7 @@ class InferenceEngine:
         out["eps"], out["pred_abs"] = r["eps"], r["pred_abs"]
         return out
 
-    def infer_host(self, plan: ScenePlan, obs_rel, pred_rel, last_obs, K: int = 20, *, chunk_scenes: int = 16384,
+    def infer_host(self, plan: ScenePlan, obs_rel, pred_rel, last_obs, K: int = 20, *, chunk_scenes: int = 8192,
                    seed: int = 0, **kw):
         """End-to-end call with HOST buffers (numpy or CPU tensors, ideally pinned): the batch is
         cut into chunks of `chunk_scenes` scenes and software-pipelined over three streams --
@@ -316,7 +320,7 @@ class InferenceEngine:
                 ready = torch.cuda.Event()
                 ready.record(s_h2d)
             main.wait_event(ready)
-            self.infer(sub, b["obs"][:n], b["pred"][:n], b["last"][:n], K, seed=seed + 0x9E3779B1 * i,
+            self.infer(sub, b["obs"][:n], b["pred"][:n], b["last"][:n], K, seed=seed + 0x9E3779B1 * i, want_vtr=False,
                        min_ade=st["d_out"][0][p_lo:p_hi], min_fde=st["d_out"][1][p_lo:p_hi], **kw)
             st["free"][i & 1].record(main)
             s_d2h.wait_event(st["free"][i & 1])
