@@ -578,21 +578,37 @@ nll_fwd_bwd_kernel(const float* __restrict__ Vpred, const float* __restrict__ Vt
 // BatchNorm running statistics: r <- (1 - m) r + m s_i, scene after scene, unbiased var.
 // 30 threads; ATen's CPU kernel evaluates the update in double, so do we.
 // ---------------------------------------------------------------------------------------
-__global__ void bn_running_update_kernel(const float* __restrict__ stats, const int32_t* __restrict__ seg_off,
-                                         int S, double momentum, float* __restrict__ bn) {
+constexpr int BN_TILE = 256;  // scenes staged per pass
+__global__ void __launch_bounds__(256)
+bn_running_update_kernel(const float* __restrict__ stats, const int32_t* __restrict__ seg_off, int S,
+                         double momentum, float* __restrict__ bn) {
+  // The recurrence is sequential in the scene index, but its inputs are not: 256 threads stage a
+  // tile of per-scene statistics (and element counts) in shared memory with coalesced loads, then
+  // 30 threads run the recurrence over the tile out of shared memory.
+  __shared__ float st[BN_TILE * SSTG_N_BN];
+  __shared__ float cnt[BN_TILE];
   const int i = threadIdx.x;
-  if (i >= SSTG_N_BN) return;
   const bool is_var = (i / 5) & 1;
-  double r = bn[i];
-  for (int s = 0; s < S; ++s) {
-    double v = stats[static_cast<size_t>(s) * SSTG_N_BN + i];
-    if (is_var) {
-      const double M = static_cast<double>(T_OBS) * (seg_off[s + 1] - seg_off[s]);
-      v = v * M / (M - 1.0);
+  double r = i < SSTG_N_BN ? static_cast<double>(bn[i]) : 0.0;
+  for (int s0 = 0; s0 < S; s0 += BN_TILE) {
+    const int ns = (S - s0 < BN_TILE) ? (S - s0) : BN_TILE;
+    for (int j = threadIdx.x; j < ns * SSTG_N_BN; j += blockDim.x) st[j] = stats[static_cast<size_t>(s0) * SSTG_N_BN + j];
+    for (int j = threadIdx.x; j < ns; j += blockDim.x)
+      cnt[j] = static_cast<float>(T_OBS * (seg_off[s0 + j + 1] - seg_off[s0 + j]));
+    __syncthreads();
+    if (i < SSTG_N_BN) {
+      for (int s = 0; s < ns; ++s) {
+        double v = st[s * SSTG_N_BN + i];
+        if (is_var) {
+          const double M = cnt[s];
+          v = v * M / (M - 1.0);
+        }
+        r = static_cast<double>(static_cast<float>(momentum * v + (1.0 - momentum) * r));
+      }
     }
-    r = static_cast<double>(static_cast<float>(momentum * v + (1.0 - momentum) * r));
+    __syncthreads();
   }
-  bn[i] = static_cast<float>(r);
+  if (i < SSTG_N_BN) bn[i] = static_cast<float>(r);
 }
 
 // grad[i] = sum over CTA rows (ascending) of the two partial buffers; parameters that are
@@ -721,7 +737,7 @@ int launch_nll_fwd_bwd(const float* Vpred, const float* Vtr, const int32_t* seg_
 int launch_bn_running_update(const float* stats, const int32_t* seg_off, int S, double momentum, float* bn,
                              cudaStream_t st) {
   if (S == 0) return SSTG_OK;
-  bn_running_update_kernel<<<1, 32, 0, st>>>(stats, seg_off, S, momentum, bn);
+  bn_running_update_kernel<<<1, 256, 0, st>>>(stats, seg_off, S, momentum, bn);
   SSTG_CUDA_TRY(cudaGetLastError(), "bn_running_update launch");
   return SSTG_OK;
 }

@@ -234,8 +234,9 @@ def test_fused_step_call_equals_separate_calls(golden, dev):
     plan = sstg.ScenePlan(n_list)
     a, b = sstg.TrainEngine(params, bn, dev), sstg.TrainEngine(params, bn, dev)
     for it in range(3):
-        la = a.step(plan, o, p, batch_size=12, lr=0.01, clip_grad=10.0)
-        lb = b.step_unfused(plan, o, p, batch_size=12, lr=0.01, clip_grad=10.0)
+        exact = bool(it & 1)                       # both graph modes
+        la = a.step(plan, o, p, batch_size=12, lr=0.01, clip_grad=10.0, graph_fp64=exact)
+        lb = b.step_unfused(plan, o, p, batch_size=12, lr=0.01, clip_grad=10.0, graph_fp64=exact)
         torch.cuda.synchronize()
         assert torch.equal(a.params, b.params) and torch.equal(a.bn, b.bn), it
         assert abs(float(la) - float(lb)) < 1e-6 * max(1.0, abs(float(lb)))
