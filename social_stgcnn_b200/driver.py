@@ -115,3 +115,46 @@ def validate_epoch(dataset, engine: E.InferenceEngine, batch_size: int = 128):
         g = loss[g0:g0 + batch_size]
         tot += float(g[:-1].sum()) / batch_size
     return tot / S
+
+
+def fit(train_set, val_set, engine: E.TrainEngine, *, num_epochs: int = 250, batch_size: int = 128, lr: float = 0.01,
+        use_lrschd: bool = False, lr_sh_rate: int = 150, clip_grad: Optional[float] = None,
+        checkpoint_dir: Optional[str] = None, args=None, seed: Optional[int] = None, trainer=None, log=print):
+    """main() of the reference (train.py:124-246) on the packed path: per epoch a shuffled
+    train_epoch and a validate_epoch, StepLR(step_size=lr_sh_rate, gamma=0.2) when `use_lrschd`,
+    and -- in `checkpoint_dir` -- exactly the artefacts the reference writes: `args.pkl`,
+    `val_best.pth` (the 40-key state_dict, on every new best validation loss), `metrics.pkl`,
+    `constant_metrics.pkl`.  Returns (metrics, constant_metrics)."""
+    import os
+    import pickle
+    rng = np.random.default_rng(seed)
+    val_eng = E.InferenceEngine(engine.params.cpu().numpy(), engine.bn.cpu().numpy(), engine.device)
+    if checkpoint_dir:
+        os.makedirs(checkpoint_dir, exist_ok=True)
+        if args is not None:
+            with open(os.path.join(checkpoint_dir, "args.pkl"), "wb") as fp:
+                pickle.dump(args, fp)
+    metrics = {"train_loss": [], "val_loss": []}
+    constant_metrics = {"min_val_epoch": -1, "min_val_loss": 9999999999999999}
+    cur_lr = lr
+    for epoch in range(num_epochs):
+        order = rng.permutation(len(train_set))                 # DataLoader(shuffle=True), train.py:173-177
+        metrics["train_loss"].append(train_epoch(train_set, engine, batch_size, cur_lr, clip_grad, order, trainer))
+        val_eng.load_weights(engine.params, engine.bn)
+        metrics["val_loss"].append(validate_epoch(val_set, val_eng, batch_size))
+        if use_lrschd and (epoch + 1) % lr_sh_rate == 0:        # StepLR.step() once per epoch, train.py:199-200,224
+            cur_lr *= 0.2
+        if metrics["val_loss"][-1] < constant_metrics["min_val_loss"]:
+            constant_metrics["min_val_loss"] = metrics["val_loss"][-1]
+            constant_metrics["min_val_epoch"] = epoch
+            if checkpoint_dir:
+                torch.save(engine.state_dict(), os.path.join(checkpoint_dir, "val_best.pth"))
+        if log:
+            log(f"epoch {epoch}: train_loss {metrics['train_loss'][-1]:.6f} val_loss {metrics['val_loss'][-1]:.6f} "
+                f"lr {cur_lr:g} {constant_metrics}")
+        if checkpoint_dir:
+            with open(os.path.join(checkpoint_dir, "metrics.pkl"), "wb") as fp:
+                pickle.dump(metrics, fp)
+            with open(os.path.join(checkpoint_dir, "constant_metrics.pkl"), "wb") as fp:
+                pickle.dump(constant_metrics, fp)
+    return metrics, constant_metrics

@@ -235,6 +235,16 @@ class InferenceEngine:
         self._cap: Dict[str, Optional[torch.Tensor]] = {}
         self._pin: Dict[tuple, Dict[str, torch.Tensor]] = {}
 
+    @classmethod
+    def from_state_dict(cls, sd, device="cuda"):
+        params, bn, _ = flatten_state_dict(sd)
+        return cls(params, bn, device)
+
+    def load_weights(self, params, bn):
+        """Replace the resident weights (e.g. with a TrainEngine's current ones) without reallocating."""
+        self.params.copy_(torch.as_tensor(params).reshape(-1))
+        self.bn.copy_(torch.as_tensor(bn).reshape(-1))
+
     def workspace(self, plan: ScenePlan) -> Dict[str, torch.Tensor]:
         """Views, sized for `plan`, of one grow-only set of device buffers (so a smaller plan --
         e.g. the chunks of infer_host -- reuses the memory of a larger one)."""
@@ -440,6 +450,59 @@ def sgd_step(params, grad, lr: float, clip_norm: float = 0.0, grad_norm_out=None
     return params
 
 
+# named_parameters() order / shapes of the reference model (model.py:157-178) and its
+# BatchNorm buffers: the layout of the flat parameter block and of bn[30].
+PARAM_LAYOUT = (
+    [("st_gcns.0.gcn.conv.weight", (5, 2, 1, 1)), ("st_gcns.0.gcn.conv.bias", (5,)),
+     ("st_gcns.0.tcn.0.weight", (5,)), ("st_gcns.0.tcn.0.bias", (5,)), ("st_gcns.0.tcn.1.weight", (1,)),
+     ("st_gcns.0.tcn.2.weight", (5, 5, 3, 1)), ("st_gcns.0.tcn.2.bias", (5,)),
+     ("st_gcns.0.tcn.3.weight", (5,)), ("st_gcns.0.tcn.3.bias", (5,)),
+     ("st_gcns.0.residual.0.weight", (5, 2, 1, 1)), ("st_gcns.0.residual.0.bias", (5,)),
+     ("st_gcns.0.residual.1.weight", (5,)), ("st_gcns.0.residual.1.bias", (5,)), ("st_gcns.0.prelu.weight", (1,)),
+     ("tpcnns.0.weight", (12, 8, 3, 3)), ("tpcnns.0.bias", (12,))]
+    + [(f"tpcnns.{k}.{w}", shp) for k in range(1, 5) for w, shp in (("weight", (12, 12, 3, 3)), ("bias", (12,)))]
+    + [("tpcnn_ouput.weight", (12, 12, 3, 3)), ("tpcnn_ouput.bias", (12,))]
+    + [(f"prelus.{k}.weight", (1,)) for k in range(5)])
+BN_MODULES = ("st_gcns.0.tcn.0", "st_gcns.0.tcn.3", "st_gcns.0.residual.1")
+
+
+def flatten_state_dict(sd):
+    """The reference's 40-key state_dict (val_best.pth) -> (params[7563], bn[30], num_batches_tracked)."""
+    params = np.concatenate([np.asarray(sd[k].detach().cpu().numpy(), np.float32).reshape(-1)
+                             for k, _ in PARAM_LAYOUT])
+    bn = np.concatenate([np.asarray(sd[f"{m}.{b}"].detach().cpu().numpy(), np.float32).reshape(-1)
+                         for m in BN_MODULES for b in ("running_mean", "running_var")])
+    nbt = int(sd.get(BN_MODULES[0] + ".num_batches_tracked", 0))
+    if params.size != L.N_PARAMS or bn.size != L.N_BN:
+        raise ValueError("state_dict does not have the reference model's shapes")
+    return params, bn, nbt
+
+
+def unflatten_state_dict(params, bn, num_batches_tracked: int = 0):
+    """(params[7563], bn[30]) -> the reference's state_dict (CPU tensors, torch.save-able as val_best.pth)."""
+    from collections import OrderedDict
+    params = np.asarray(params, np.float32).reshape(-1)
+    bn = np.asarray(bn, np.float32).reshape(-1)
+    flat, off = {}, 0
+    for k, shp in PARAM_LAYOUT:
+        n = int(np.prod(shp))
+        flat[k] = torch.from_numpy(params[off:off + n].reshape(shp).copy())
+        off += n
+    bnt = {}
+    for i, m in enumerate(BN_MODULES):
+        bnt[m + ".running_mean"] = torch.from_numpy(bn[10 * i:10 * i + 5].copy())
+        bnt[m + ".running_var"] = torch.from_numpy(bn[10 * i + 5:10 * i + 10].copy())
+        bnt[m + ".num_batches_tracked"] = torch.tensor(int(num_batches_tracked))
+    sd = OrderedDict()                      # nn.Module.state_dict() order: a module's params, then its buffers
+    for k, _ in PARAM_LAYOUT:
+        sd[k] = flat[k]
+        mod = k.rsplit(".", 1)[0]
+        if mod in BN_MODULES and k.endswith(".bias"):
+            for b in ("running_mean", "running_var", "num_batches_tracked"):
+                sd[f"{mod}.{b}"] = bnt[f"{mod}.{b}"]
+    return sd
+
+
 def group_weights(S: int, batch_size: int) -> np.ndarray:
     """Loss weights of one optimiser group of train() (train.py:58-66): every scene but the
     last is scored with weight 1/batch_size; the last one is forwarded (it updates the BN
@@ -470,6 +533,16 @@ class TrainEngine:
         self.num_batches_tracked = int(num_batches_tracked)
         self.grad = torch.zeros(L.N_PARAMS, dtype=torch.float32, device=device)
         self._ws: Dict[str, torch.Tensor] = {}
+
+    @classmethod
+    def from_state_dict(cls, sd, device="cuda"):
+        params, bn, nbt = flatten_state_dict(sd)
+        return cls(params, bn, device, nbt)
+
+    def state_dict(self):
+        """The reference's state_dict (40 keys) of the current weights: `torch.save(eng.state_dict(),
+        'val_best.pth')` is loadable by the reference's test.py:183-186 unchanged."""
+        return unflatten_state_dict(self.params.cpu().numpy(), self.bn.cpu().numpy(), self.num_batches_tracked)
 
     def forward_backward(self, plan: ScenePlan, obs_rel, pred_rel, scene_weight, *, graph_fp64: bool = True):
         """Everything of a group except the parameter update.  Returns dict(loss[S], grad[7563],

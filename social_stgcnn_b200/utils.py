@@ -73,6 +73,18 @@ def poly_fit(traj, traj_len, threshold):
     return 1.0 if res_x + res_y >= threshold else 0.0
 
 
+def _poly_fit_batch(seq, traj_len, threshold):
+    """poly_fit (utils.py:56-71) for every pedestrian of a window in two least-squares solves:
+    np.polyfit accepts a 2-D right-hand side, so the residuals come from the same LAPACK path."""
+    n = seq.shape[0]
+    t = np.linspace(0, traj_len - 1, traj_len)
+    res_x = np.polyfit(t, seq[:, 0, -traj_len:].T, 2, full=True)[1]
+    res_y = np.polyfit(t, seq[:, 1, -traj_len:].T, 2, full=True)[1]
+    if res_x.size != n or res_y.size != n:      # rank-deficient fit returns no residuals; mirror the scalar path
+        return np.array([poly_fit(s, traj_len, threshold) for s in seq])
+    return (res_x + res_y >= threshold).astype(np.float64)
+
+
 def read_file(_path, delim="\t"):
     """utils.py:72-83: rows of `<frame> <ped> <x> <y>`; ValueError on a wrong delimiter."""
     delim = {"tab": "\t", "space": " "}.get(delim, delim)
@@ -114,7 +126,7 @@ def _scenes_of_file(data, seq_len, skip, min_ped, pred_len, threshold):
         seq = xy[rowid[sel, idx:idx + seq_len]].transpose(0, 2, 1)   # (n, 2, L)
         rel = np.zeros_like(seq)
         rel[:, :, 1:] = seq[:, :, 1:] - seq[:, :, :-1]              # utils.py:153-155
-        nl = np.array([poly_fit(s, pred_len, threshold) for s in seq])
+        nl = _poly_fit_batch(seq, pred_len, threshold)
         yield seq, rel, nl, seen
 
 

@@ -233,3 +233,32 @@ def test_driver_train_epoch_vs_oracle(golden, dev):
     assert np.abs(w - flat).max() < 1e-5 * np.abs(flat).max()
     assert np.allclose(eng.bn.cpu().numpy(), O.flatten_bn(S), rtol=1e-5, atol=1e-7)
     assert eng.num_batches_tracked == 8
+
+
+def test_driver_fit_writes_reference_artifacts(golden, dev, tmp_path):
+    """driver.fit (main() of train.py): two epochs on the eth/test split; the artefacts are the
+    reference's (args.pkl, val_best.pth with the 40-key state_dict, metrics.pkl,
+    constant_metrics.pkl) and the checkpoint loads into the drop-in module and reproduces the
+    engine's validation loss."""
+    import pickle
+    import social_stgcnn_b200 as sstg
+    from social_stgcnn_b200 import driver
+    from social_stgcnn_b200.model import social_stgcnn
+    from social_stgcnn_b200.utils import TrajectoryDataset
+    d = TrajectoryDataset(os.path.join(GOLD, "datasets", "eth", "test") + "/", obs_len=8, pred_len=12, skip=1,
+                          norm_lap_matr=True, device=dev)
+    params, bn = golden.params("eth")
+    eng = sstg.TrainEngine(params, bn, dev, num_batches_tracked=int(golden.weights["eth.nbt"][0]))
+    ck = str(tmp_path / "ck") + "/"
+    metrics, const = driver.fit(d, d, eng, num_epochs=2, batch_size=16, lr=0.01, use_lrschd=True, lr_sh_rate=1,
+                                checkpoint_dir=ck, args={"tag": "t"}, seed=0, log=None)
+    assert len(metrics["train_loss"]) == 2 and all(np.isfinite(metrics["val_loss"]))
+    assert sorted(os.listdir(ck)) == ["args.pkl", "constant_metrics.pkl", "metrics.pkl", "val_best.pth"]
+    assert pickle.load(open(ck + "metrics.pkl", "rb")) == metrics
+    sd = torch.load(ck + "val_best.pth")
+    m = social_stgcnn(n_stgcnn=1, n_txpcnn=5, output_feat=5, seq_len=8, kernel_size=3, pred_seq_len=12)
+    m.load_state_dict(sd, strict=True)
+    best = const["min_val_epoch"]
+    ie = sstg.InferenceEngine.from_state_dict(sd, dev)
+    assert abs(driver.validate_epoch(d, ie, 16) - metrics["val_loss"][best]) < 1e-6
+    assert int(sd["st_gcns.0.tcn.0.num_batches_tracked"]) == int(golden.weights["eth.nbt"][0]) + 70 * (best + 1)

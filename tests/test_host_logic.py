@@ -77,3 +77,30 @@ def test_group_weights():
     assert w.dtype == np.float32 and w[-1] == 0 and np.all(w[:-1] == np.float32(1 / 128))
     assert list(group_weights(3, 4)) == [0.25, 0.25, 0.0]        # short trailing group keeps the divisor
     assert group_weights(0, 4).size == 0
+
+
+def test_state_dict_roundtrip_and_order(golden):
+    """flat block <-> the reference's 40-key state_dict, in nn.Module.state_dict() order, so
+    torch.save(engine.state_dict()) is a drop-in val_best.pth."""
+    from oracle import stgcnn_oracle as O
+    from social_stgcnn_b200 import engine as E
+    from social_stgcnn_b200.model import social_stgcnn
+    assert [(k, tuple(s)) for k, s in E.PARAM_LAYOUT] == [(k, tuple(s)) for k, s in O.PARAM_LAYOUT]
+    params, bn = golden.params("zara1")
+    sd = E.unflatten_state_dict(params, bn, 123)
+    m = social_stgcnn(n_stgcnn=1, n_txpcnn=5, output_feat=5, seq_len=8, kernel_size=3, pred_seq_len=12)
+    assert list(sd.keys()) == list(m.state_dict().keys())
+    m.load_state_dict(sd, strict=True)
+    p2, b2, nbt = E.flatten_state_dict(m.state_dict())
+    assert np.array_equal(p2, params) and np.array_equal(b2, bn) and nbt == 123
+    assert np.array_equal(m._flat_params().detach().numpy(), params)
+
+
+def test_batched_poly_fit_equals_scalar():
+    from social_stgcnn_b200.utils import _poly_fit_batch, poly_fit
+    rng = np.random.default_rng(3)
+    seq = rng.normal(0, 1, (64, 2, 20)).cumsum(2) * 0.02
+    seq[5] = np.linspace(0, 1, 20)[None] * np.array([[1.0], [2.0]])           # exactly linear -> 0
+    got = _poly_fit_batch(seq, 12, 0.002)
+    ref = np.array([poly_fit(s, 12, 0.002) for s in seq])
+    assert np.array_equal(got, ref) and got[5] == 0.0 and 0 < got.mean() < 1
