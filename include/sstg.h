@@ -66,7 +66,9 @@ const char* sstg_last_cuda_error(void);
 
 /* ---- host-side planning (pure CPU, no CUDA) ---------------------------------------
  * From the per-scene pedestrian counts compute the packed-batch offsets and the
- * TXP-CNN tile table.  seg_off_host[S+1], a_off_host[S+1], tile_off_host[S+1] are
+ * TXP-CNN tile table (whole scenes per tile; at most SSTG_XTILE_COLS columns and
+ * SSTG_XTILE_MAX_SCENES scenes, narrower -- down to 8 columns -- for batches too small to
+ * fill the GPU with full tiles: cap = clamp(ceil(P / 296), 8, 128)).  seg_off_host[S+1], a_off_host[S+1], tile_off_host[S+1] are
  * caller-provided; tile t covers scenes [tile_off[t], tile_off[t+1]).
  * Outputs *n_tiles, *max_n, *a_floats (total floats of the packed A buffer, padded).
  * Replaces the `seq_start_end` bookkeeping of TrajectoryDataset (utils.py:186-190). */

@@ -43,6 +43,13 @@ int sstg_plan_host(const int32_t* n_peds_host, int32_t S, int32_t T, int32_t* se
   if (S < 0 || T <= 0 || (S > 0 && !n_peds_host) || !seg_off_host || !a_off_host || !tile_off_host || !n_tiles ||
       !max_n || !a_floats)
     return SSTG_EINVAL;
+  // TXP-CNN tile width: whole scenes up to SSTG_XTILE_COLS columns -- but a SMALL batch is cut into
+  // narrower tiles so that it still spreads over the SMs (a tile is one CTA): aim at two tiles per
+  // SM of a 148-SM part, never below 8 columns.  Large batches get the full 128-column tiles.
+  int64_t total = 0;
+  for (int32_t s = 0; s < S; ++s) total += n_peds_host[s] > 0 ? n_peds_host[s] : 0;
+  int64_t cap64 = (total + 295) / 296;
+  const int32_t cap = static_cast<int32_t>(cap64 < 8 ? 8 : (cap64 > SSTG_XTILE_COLS ? SSTG_XTILE_COLS : cap64));
   int64_t ped = 0, af = 0;
   int32_t mx = 0, nt = 0, cols = 0, scenes = 0;
   seg_off_host[0] = 0;
@@ -54,7 +61,7 @@ int sstg_plan_host(const int32_t* n_peds_host, int32_t S, int32_t T, int32_t* se
     if (n > SSTG_MAX_PEDS) return SSTG_ETOOBIG;
     if (n > mx) mx = n;
     // close the current TXP-CNN tile if this scene does not fit any more
-    if (scenes > 0 && (cols + n > SSTG_XTILE_COLS || scenes == SSTG_XTILE_MAX_SCENES)) {
+    if (scenes > 0 && (cols + n > cap || scenes == SSTG_XTILE_MAX_SCENES)) {
       tile_off_host[++nt] = s;
       cols = 0;
       scenes = 0;

@@ -50,28 +50,31 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
-// dW[hf*6 + co][ci][kh][kw] += sum_{h, c} du[hf*6+co][h][c] * x[ci][h+kh-1][c+kw-1] over the tile's columns
+// dW[hf*6 + co][ci][kh][kw] += sum_{h, c} du[hf*6+co][h][c] * x[ci][h+kh-1][c+kw-1] over the tile's columns.
+// Packed FMAs over channel pairs: acc[pr][tap] = (dW[2pr][tap], dW[2pr+1][tap]).
 __device__ __forceinline__ void dw_unit(const float* __restrict__ DU, const float* __restrict__ XT, int Wp,
                                         int c_end, int ci, int hf, int cin, int lane, float* __restrict__ gw) {
-  float acc[6][9];
+  float2 acc[3][9];
 #pragma unroll
-  for (int co = 0; co < 6; ++co)
+  for (int pr = 0; pr < 3; ++pr)
 #pragma unroll
-    for (int k = 0; k < 9; ++k) acc[co][k] = 0.f;
+    for (int k = 0; k < 9; ++k) acc[pr][k] = make_float2(0.f, 0.f);
   for (int c = 1 + lane; c <= c_end; c += 32) {
-    float x[5][3];
+    float2 x[5][3];
     const float* xp = XT + (ci * 5) * Wp + c - 1;
 #pragma unroll
-    for (int h = 0; h < 5; ++h) {
-      x[h][0] = xp[h * Wp];
-      x[h][1] = xp[h * Wp + 1];
-      x[h][2] = xp[h * Wp + 2];
-    }
+    for (int h = 0; h < 5; ++h)
 #pragma unroll
-    for (int co = 0; co < 6; ++co) {
-      float d[5];
+      for (int kw = 0; kw < 3; ++kw) {
+        const float v = xp[h * Wp + kw];
+        x[h][kw] = make_float2(v, v);
+      }
 #pragma unroll
-      for (int h = 0; h < 5; ++h) d[h] = DU[((hf * 6 + co) * 5 + h) * Wp + c];
+    for (int pr = 0; pr < 3; ++pr) {
+      float2 d[5];
+#pragma unroll
+      for (int h = 0; h < 5; ++h)
+        d[h] = make_float2(DU[((hf * 6 + 2 * pr) * 5 + h) * Wp + c], DU[((hf * 6 + 2 * pr + 1) * 5 + h) * Wp + c]);
 #pragma unroll
       for (int kh = 0; kh < 3; ++kh)
 #pragma unroll
@@ -79,16 +82,19 @@ __device__ __forceinline__ void dw_unit(const float* __restrict__ DU, const floa
 #pragma unroll
           for (int h = 0; h < 5; ++h) {
             const int hi = h + kh - 1;
-            if (hi >= 0 && hi < 5) acc[co][kh * 3 + kw] = fmaf(d[h], x[hi][kw], acc[co][kh * 3 + kw]);
+            if (hi >= 0 && hi < 5) ffma2(acc[pr][kh * 3 + kw], d[h], x[hi][kw]);
           }
     }
   }
 #pragma unroll
-  for (int co = 0; co < 6; ++co)
+  for (int pr = 0; pr < 3; ++pr)
 #pragma unroll
     for (int k = 0; k < 9; ++k) {
-      const float s = warp_sum(acc[co][k]);
-      if (lane == 0) gw[((hf * 6 + co) * cin + ci) * 9 + k] += s;
+      const float s0 = warp_sum(acc[pr][k].x), s1 = warp_sum(acc[pr][k].y);
+      if (lane == 0) {
+        gw[((hf * 6 + 2 * pr) * cin + ci) * 9 + k] += s0;
+        gw[((hf * 6 + 2 * pr + 1) * cin + ci) * 9 + k] += s1;
+      }
     }
 }
 
@@ -107,14 +113,15 @@ txpcnn_bwd_kernel(const float* __restrict__ dOut, const float* __restrict__ Usav
   const int half = tid / X_COLS;
   const int qt = tid - half * X_COLS;
 
-  // ---- transposed + flipped weights: wT[l][(b*2 + hf)*56 + a6*9 + tap'] = W_l[b][hf*6 + a6][8 - tap']
+  // ---- transposed + flipped weights, tap-major for the packed column convolution:
+  //      wT[l][(b*2 + hf)*56 + tap'*6 + a6] = W_l[b][hf*6 + a6][8 - tap']
   for (int i = tid; i < B_WT; i += X_THREADS) {
     const int l = i / X_WL, r = i % X_WL;
     const int b = r / (2 * X_WSLOT), r2 = r % (2 * X_WSLOT);
     const int hf = r2 / X_WSLOT, r3 = r2 % X_WSLOT;
     float v = 0.f;
     if (r3 < 54) {
-      const int a = hf * 6 + r3 / 9, tap = r3 % 9;
+      const int a = hf * 6 + r3 % 6, tap = r3 / 6;
       const int cin = (l == 0) ? 8 : 12;
       if (a < cin) v = params[w_base(l) + (b * cin + a) * 9 + (8 - tap)];
     }
@@ -150,7 +157,7 @@ txpcnn_bwd_kernel(const float* __restrict__ dOut, const float* __restrict__ Usav
     int sc[JX], gN[JX];
     long long gO[JX];
     bool on[JX];
-    float G[JX][6][5];
+    float2 G[JX][3][5];  // dL/dx of this thread's (channel pair, feature row), both columns
 #pragma unroll
     for (int u = 0; u < JX; ++u) {
       const int q = qt + u * X_COLS;
@@ -166,7 +173,7 @@ txpcnn_bwd_kernel(const float* __restrict__ dOut, const float* __restrict__ Usav
         for (int h = 0; h < 5; ++h) {
           const int row = (half * 6 + co) * 5 + h;
           const float g = on[u] ? dOut[gO[u] + static_cast<long long>(row) * gN[u]] : 0.f;
-          G[u][co][h] = g;
+          (co & 1 ? G[u][co >> 1][h].y : G[u][co >> 1][h].x) = g;
           if (on[u]) DU[row * Wp + sc[u]] = g;
         }
     }
@@ -196,14 +203,14 @@ txpcnn_bwd_kernel(const float* __restrict__ dOut, const float* __restrict__ Usav
         if (lane == 0) gacc[b_base(l) - P_TP0_W + co] += sb_;
       }
       // ---- transposed convolution: T = conv_l^T(du_l)
-      float T[JX][6][5];
+      float2 T[JX][3][5];
 #pragma unroll
       for (int u = 0; u < JX; ++u) {
 #pragma unroll
-        for (int co = 0; co < 6; ++co)
+        for (int pr = 0; pr < 3; ++pr)
 #pragma unroll
-          for (int h = 0; h < 5; ++h) T[u][co][h] = 0.f;
-        if (on[u]) conv_column<12>(DU, Wp, sc[u], sm.wT + l * X_WL, half, T[u]);
+          for (int h = 0; h < 5; ++h) T[u][pr][h] = make_float2(0.f, 0.f);
+        if (on[u]) conv_column2<12>(DU, Wp, sc[u], sm.wT + l * X_WL, half, T[u]);
       }
       __syncthreads();  // every read of DU / XT for layer l is done
       if (l == 0) {
@@ -218,7 +225,7 @@ txpcnn_bwd_kernel(const float* __restrict__ dOut, const float* __restrict__ Usav
 #pragma unroll
               for (int h = 0; h < 5; ++h) {
                 const int row = (half * 6 + co) * 5 + h;
-                if (row < 40) o[static_cast<long long>(row) * gN[u]] = T[u][co][h];
+                if (row < 40) o[static_cast<long long>(row) * gN[u]] = (co & 1) ? T[u][co >> 1][h].y : T[u][co >> 1][h].x;
               }
           }
         break;
@@ -231,8 +238,10 @@ txpcnn_bwd_kernel(const float* __restrict__ dOut, const float* __restrict__ Usav
         for (int co = 0; co < 6; ++co)
 #pragma unroll
           for (int h = 0; h < 5; ++h) {
-            const float g = (l == 4) ? T[u][co][h] : G[u][co][h] + T[u][co][h];
-            G[u][co][h] = g;
+            float& Gr = (co & 1) ? G[u][co >> 1][h].y : G[u][co >> 1][h].x;
+            const float Tv = (co & 1) ? T[u][co >> 1][h].y : T[u][co >> 1][h].x;
+            const float g = (l == 4) ? Tv : Gr + Tv;
+            Gr = g;
             if (on[u]) {
               const int row = (half * 6 + co) * 5 + h;
               const float uv = Usave[k * layer_stride + gO[u] + static_cast<long long>(row) * gN[u]];

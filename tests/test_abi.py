@@ -50,11 +50,14 @@ def test_plan_host_offsets_and_tiles(lib):
     for i, k in enumerate(n):
         assert p.a_off[i] % 4 == 0 and p.a_off[i + 1] - p.a_off[i] >= 8 * k * k
     assert p.a_floats == p.a_off[-1]
-    # tiles: whole scenes, <= 128 columns unless a single scene is larger
-    assert list(p.tile_off) == [0, 3, 5, 6, 7] and p.n_tiles == 4
+    # tiles: whole scenes; column cap = clamp(ceil(P / 296), 8, 128) unless a single scene is larger
+    cap = min(128, max(8, -(-p.P // 296)))
+    assert cap == 8 and list(p.tile_off) == [0, 2, 3, 4, 5, 6, 7] and p.n_tiles == 6
     for t in range(p.n_tiles):
         cols = p.seg_off[p.tile_off[t + 1]] - p.seg_off[p.tile_off[t]]
-        assert cols <= 128 or p.tile_off[t + 1] - p.tile_off[t] == 1
+        assert cols <= cap or p.tile_off[t + 1] - p.tile_off[t] == 1
+    big = sstg.ScenePlan([64] * 4096)                       # a large batch gets the full 128-column tiles
+    assert big.n_tiles == 2048 and np.all(np.diff(big.tile_off) == 2)
 
 
 def test_plan_host_many_tiny_scenes_cap(lib):
