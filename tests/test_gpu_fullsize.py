@@ -127,3 +127,64 @@ def test_dense_crowds_properties(golden, dev):
         oa, of, _ = O.sample_ade_fde(got.transpose(1, 2, 0), vt, last[sl], eps[s].cpu().numpy())
         assert np.abs(rx["min_ade"][sl].cpu().numpy() - oa).max() < 2e-6 * max(1.0, oa.max()), s
         assert np.abs(rx["min_fde"][sl].cpu().numpy() - of).max() < 2e-6 * max(1.0, of.max()), s
+
+
+def test_large_scenes_256_pedestrians(golden, dev):
+    """BASELINE config 4: 256 pedestrians per scene (the N x N aggregation stress; one A[t] slice is
+    256 KB > shared memory, so st_gcn streams it in row chunks; TXP-CNN tiles are single scenes).
+    Mixed with 200 / 129 / 128 / 65 to cross every kernel-variant boundary.  Graph bit-exact in
+    fp64 mode, forward / NLL / ADE / FDE against the oracle, and one training group against the
+    fp64 oracle."""
+    import social_stgcnn_b200 as sstg
+    from social_stgcnn_b200 import engine as E
+    from oracle import stgcnn_oracle as O
+    n_list = [256, 200, 129, 128, 65, 256, 3]
+    obs_rel, pred_rel, obs_abs = O.synthetic_scenes(1, sum(n_list), seed=256)
+    last = np.ascontiguousarray(obs_abs[:, :, -1])
+    plan = sstg.ScenePlan(n_list)
+    params, bn = golden.params("univ") if "univ.params" in golden.weights.files else golden.params("eth")
+    eng = sstg.InferenceEngine(params, bn, dev)
+    obs, pred, lst = (torch.from_numpy(a).to(dev) for a in (obs_rel, pred_rel, last))
+    rx = eng.infer(plan, obs, pred, lst, K=20, seed=4, graph_fp64=True, fp64_dist=True, want_eps=True)
+    loss = sstg.nll_forward(plan.on(dev), rx["V_pred"], rx["V_tr"])
+    rf = eng.infer(plan, obs, pred, lst, K=20, seed=4)          # fast modes, separate call (workspace reuse)
+    torch.cuda.synchronize()
+    A_fast = rf["A_obs"].cpu().numpy()
+    rx2 = eng.infer(plan, obs, pred, lst, K=20, seed=4, graph_fp64=True, fp64_dist=True, want_eps=True)
+    torch.cuda.synchronize()
+    A, vp, eps = rx2["A_obs"].cpu().numpy(), rx2["V_pred"].cpu().numpy(), rx2["eps"].cpu().numpy()
+    ade, fde = rx2["min_ade"].cpu().numpy(), rx2["min_fde"].cpu().numpy()
+    P_, S_ = O.unflatten_params(params), O.unflatten_bn(bn)
+    for i, n in enumerate(n_list):
+        o, ao = int(plan.seg_off[i]), int(plan.a_off[i])
+        V_ref, A_ref = O.seq_to_graph(obs_rel[o:o + n])
+        a = A[ao:ao + 8 * n * n].reshape(8, n, n)
+        assert np.array_equal(a.view(np.uint32), A_ref.view(np.uint32)), n
+        af = A_fast[ao:ao + 8 * n * n].reshape(8, n, n).astype(np.float64)
+        assert np.array_equal(af == 0, A_ref == 0)
+        assert (np.abs(af - A_ref) / np.maximum(np.abs(A_ref), 1e-3)).max() < 3e-6, n
+        with torch.no_grad():
+            out = O.model_forward(P_, S_, V_ref, A_ref)
+        got = vp[o * 60:(o + n) * 60].reshape(1, 5, 12, n)
+        assert rel_err(got, out.numpy()) < 1e-5, n
+        vt = np.ascontiguousarray(pred_rel[o:o + n].transpose(2, 0, 1))
+        l_ref = float(O.bivariate_loss(O.vpred_tn5(out), torch.from_numpy(vt)))
+        assert abs(float(loss[i]) - l_ref) < 1e-5 * max(1.0, abs(l_ref)), n
+        e = eps[o * 480:(o + n) * 480].reshape(20, 12, n, 2)
+        oa, of, _ = O.sample_ade_fde(got[0].transpose(1, 2, 0), vt, last[o:o + n], e)
+        assert np.abs(ade[o:o + n] - oa).max() < 2e-6 * max(1.0, oa.max()), n
+        assert np.abs(fde[o:o + n] - of).max() < 2e-6 * max(1.0, of.max()), n
+    # one optimiser group at these sizes against the fp64 oracle
+    tr = sstg.TrainEngine(params, bn, dev)
+    r = tr.forward_backward(plan, obs, pred, E.group_weights(len(n_list), 8))
+    torch.cuda.synchronize()
+    scenes = []
+    for i, n in enumerate(n_list):
+        o = int(plan.seg_off[i])
+        V, A_ = O.seq_to_graph(obs_rel[o:o + n])
+        scenes.append((V, A_, np.ascontiguousarray(pred_rel[o:o + n].transpose(2, 0, 1))))
+    lo, go, _, _ = O.train_step(O.unflatten_params(params, torch.float64), O.unflatten_bn(bn, torch.float64), scenes, 8)
+    got_loss = float((r["loss"].double() * r["weight"].double()).sum())
+    assert abs(got_loss - lo) < 1e-5 * max(1.0, abs(lo))
+    g = r["grad"].cpu().numpy().astype(np.float64)
+    assert np.abs(g - go).max() < 5e-5 * np.abs(go).max()
