@@ -149,6 +149,18 @@ int sstg_rel_to_abs(const float* rel, const double* init, const int32_t* seg_off
 int sstg_traj_error(const float* pred, const float* tgt, const int32_t* seg_off, int32_t S,
                     int32_t total_peds, int32_t T, double* sum_dist, double* final_dist, void* stream);
 
+/* ---- compact host format (input side of the path) ---------------------------------------
+ * The dataset's positions are 4-decimal numbers (utils.py:145), so a 20-frame track is exactly
+ * an int32 start position plus 19 int16 steps, both in units of 1e-4: 88 bytes per pedestrian
+ * instead of the 168 bytes of obs_traj_rel + pred_traj_rel + obs_traj[:, :, -1] in fp32.
+ * sstg_decode_tracks reproduces those three tensors BIT FOR BIT on the device (float64 k/1e4 and
+ * differences, cast to fp32: utils.py:145,153-155,180-183), halving the PCIe traffic of a
+ * host-fed evaluation.
+ *   start [P,2] int32;  delta [P,2,20] int16 (delta[.,.,0] ignored, 16-byte rows for alignment)
+ *   obs_rel [P,2,8], pred_rel [P,2,12], last_obs [P,2]  fp32 outputs */
+int sstg_decode_tracks(const int32_t* start, const int16_t* delta, int32_t total_peds,
+                       float* obs_rel, float* pred_rel, float* last_obs, void* stream);
+
 /* ===================== training path (train.py:28-79) =================================
  * The reference trains with batch 1 and accumulates the loss of `batch_size` scenes before
  * one backward (train.py:58-74).  A packed batch reproduces that exactly: BatchNorm uses

@@ -427,6 +427,60 @@ __global__ void traj_error_kernel(const float* __restrict__ pred, const float* _
 
 }  // namespace
 
+namespace {
+// Compact host format -> the fp32 tensors of TrajectoryDataset, bit for bit.
+// The dataset's positions are decimal numbers with 4 places (utils.py:145 np.around(.., 4) =
+// rint(x * 1e4) / 1e4 in float64), so a track is exactly: an int32 start (units of 1e-4) plus 19
+// int16 steps.  Decoding repeats the reference's arithmetic: pos64 = k / 1e4 (float64 division),
+// rel = fp32(pos64[t] - pos64[t-1]) (utils.py:153-155,180-183), last_obs = fp32(pos64[7]).
+// One thread per (pedestrian, coordinate); 20 frames = obs 8 + pred 12.
+__global__ void decode_tracks_kernel(const int32_t* __restrict__ start, const int16_t* __restrict__ delta, int P,
+                                     float* __restrict__ obs_rel, float* __restrict__ pred_rel,
+                                     float* __restrict__ last_obs) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;  // p*2 + c
+  if (i >= 2 * P) return;
+  const int2* dp = reinterpret_cast<const int2*>(delta + static_cast<size_t>(i) * 20);  // 40 bytes, 8-byte aligned
+  int16_t d[20];
+#pragma unroll
+  for (int q = 0; q < 5; ++q) {
+    const int2 v = dp[q];
+    d[4 * q] = static_cast<int16_t>(v.x & 0xffff);
+    d[4 * q + 1] = static_cast<int16_t>(v.x >> 16);
+    d[4 * q + 2] = static_cast<int16_t>(v.y & 0xffff);
+    d[4 * q + 3] = static_cast<int16_t>(v.y >> 16);
+  }
+  int k = start[i];
+  double prev = static_cast<double>(k) / 10000.0;
+  float r[20];
+  r[0] = 0.f;  // utils.py:153: the first relative displacement is zero
+  float last = static_cast<float>(prev);
+#pragma unroll
+  for (int t = 1; t < 20; ++t) {
+    k += d[t];
+    const double cur = static_cast<double>(k) / 10000.0;
+    r[t] = static_cast<float>(cur - prev);
+    prev = cur;
+    if (t == T_OBS - 1) last = static_cast<float>(cur);
+  }
+  float4* o = reinterpret_cast<float4*>(obs_rel + static_cast<size_t>(i) * T_OBS);
+  o[0] = make_float4(r[0], r[1], r[2], r[3]);
+  o[1] = make_float4(r[4], r[5], r[6], r[7]);
+  float4* q = reinterpret_cast<float4*>(pred_rel + static_cast<size_t>(i) * T_PRED);
+  q[0] = make_float4(r[8], r[9], r[10], r[11]);
+  q[1] = make_float4(r[12], r[13], r[14], r[15]);
+  q[2] = make_float4(r[16], r[17], r[18], r[19]);
+  last_obs[i] = last;
+}
+}  // namespace
+
+int launch_decode_tracks(const int32_t* start, const int16_t* delta, int P, float* obs_rel, float* pred_rel,
+                         float* last_obs, cudaStream_t st) {
+  if (P == 0) return SSTG_OK;
+  decode_tracks_kernel<<<(2 * P + 255) / 256, 256, 0, st>>>(start, delta, P, obs_rel, pred_rel, last_obs);
+  SSTG_CUDA_TRY(cudaGetLastError(), "decode_tracks launch");
+  return SSTG_OK;
+}
+
 int launch_rel_to_abs(const float* rel, const double* init, const int32_t* seg_off, int S, int P, int T, float* out,
                       cudaStream_t st) {
   if (S == 0 || P == 0) return SSTG_OK;

@@ -44,7 +44,24 @@ __device__ __forceinline__ double weight(float s, double) {
   const double nrm = sqrt(static_cast<double>(s));  // math.sqrt (utils.py:24)
   return nrm == 0.0 ? 0.0 : 1.0 / nrm;              // utils.py:25-27
 }
-__device__ __forceinline__ float weight(float s, float) { return s > 0.f ? rsqrtf(s) : 0.f; }
+__device__ __forceinline__ float rsqrt_fast(float x) {
+  float y;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// inverse distance from the squared distance; a squared distance below FLT_MIN (only the
+// exact-zero case occurs with real coordinates) is the reference's "distance 0 -> weight 0"
+__device__ __forceinline__ float inv_dist(float sq) { return sq >= 1.17549435e-38f ? rsqrt_fast(sq) : 0.f; }
+
+// fp32 mode: one FMA for the squared distance, one MUFU for the inverse distance
+__device__ __forceinline__ float weight(float s, float) { return inv_dist(s); }
+__device__ __forceinline__ float sqdist_mode(float xh, float yh, float xk, float yk, float) {
+  const float dx = xh - xk, dy = yh - yk;
+  return fmaf(dx, dx, dy * dy);
+}
+__device__ __forceinline__ float sqdist_mode(float xh, float yh, float xk, float yk, double) {
+  return sqdist(xh, yh, xk, yk);
+}
 
 template <bool F64, int NJ>
 __global__ void __launch_bounds__(G_THREADS)
@@ -101,7 +118,7 @@ graph_build_kernel(const float* __restrict__ rel, const int32_t* __restrict__ se
               const float xh = xt[h], yh = yt[h];
 #pragma unroll
               for (int j = 0; j < NJ; ++j) {
-                Real w = weight(sqdist(xh, yh, xk[j], yk[j]), Real(0));
+                Real w = weight(sqdist_mode(xh, yh, xk[j], yk[j], Real(0)), Real(0));
                 if (h == lane + 32 * j) w = Real(1);
                 dk[j] += w;
               }
@@ -118,13 +135,13 @@ graph_build_kernel(const float* __restrict__ rel, const int32_t* __restrict__ se
               for (int u = 0; u < 4; ++u) {
                 const float xh = xt[h + u], yh = yt[h + u];
 #pragma unroll
-                for (int j = 0; j < NJ; ++j) acc[j][u] += weight(sqdist(xh, yh, xk[j], yk[j]), Real(0));
+                for (int j = 0; j < NJ; ++j) acc[j][u] += weight(sqdist_mode(xh, yh, xk[j], yk[j], Real(0)), Real(0));
               }
             }
             for (; h < N; ++h) {
               const float xh = xt[h], yh = yt[h];
 #pragma unroll
-              for (int j = 0; j < NJ; ++j) acc[j][0] += weight(sqdist(xh, yh, xk[j], yk[j]), Real(0));
+              for (int j = 0; j < NJ; ++j) acc[j][0] += weight(sqdist_mode(xh, yh, xk[j], yk[j], Real(0)), Real(0));
             }
             // the diagonal contributed w(0) = 0; d = 1 + off-diagonal sum
 #pragma unroll
@@ -136,7 +153,7 @@ graph_build_kernel(const float* __restrict__ rel, const int32_t* __restrict__ se
 #pragma unroll
           for (int j = 0; j < NJ; ++j) {
             const int k = lane + 32 * j;
-            dsk[j] = F64 ? Real(1.0 / sqrt(static_cast<double>(dk[j]))) : Real(rsqrtf(static_cast<float>(dk[j])));
+            dsk[j] = F64 ? Real(1.0 / sqrt(static_cast<double>(dk[j]))) : Real(rsqrt_fast(static_cast<float>(dk[j])));
             if (k < N) dsw[k] = dsk[j];
           }
           __syncwarp();
@@ -149,9 +166,13 @@ graph_build_kernel(const float* __restrict__ rel, const int32_t* __restrict__ se
 #pragma unroll
           for (int j = 0; j < NJ; ++j) {
             const int k = lane + 32 * j;
-            const Real w = weight(sqdist(xh, yh, xk[j], yk[j]), Real(0));
+            const Real w = weight(sqdist_mode(xh, yh, xk[j], yk[j], Real(0)), Real(0));
             float a;
-            if (norm_lap) {
+            if (norm_lap && !F64) {
+              // -(w ds_h) ds_k + 0: the fused form yields +0.0 for absent edges without a select
+              const float wv = (h == k) ? -static_cast<float>(lkk[j]) : static_cast<float>(w);
+              a = fmaf(-(wv * static_cast<float>(dsh)), static_cast<float>(dsk[j]), 0.f);
+            } else if (norm_lap) {
               const Real l = (h == k) ? lkk[j] : -w;
               a = static_cast<float>(dsh * (l * dsk[j]));
               if (h != k && w == Real(0)) a = 0.f;  // absent edge: +0.0, not -0.0
@@ -179,15 +200,6 @@ graph_build_kernel(const float* __restrict__ rel, const int32_t* __restrict__ se
 // ---------------------------------------------------------------------------------------
 constexpr int F_WARPS = 4;
 constexpr int F_THREADS = F_WARPS * 32;
-
-__device__ __forceinline__ float rsqrt_fast(float x) {
-  float y;
-  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-// inverse distance from the squared distance; a squared distance below FLT_MIN (only the
-// exact-zero case occurs with real coordinates) is the reference's "distance 0 -> weight 0"
-__device__ __forceinline__ float inv_dist(float sq) { return sq >= 1.17549435e-38f ? rsqrt_fast(sq) : 0.f; }
 
 // Requires T % 4 == 0 (8 and 12 in every configuration) and N <= 64.
 template <int NJ>

@@ -150,6 +150,16 @@ int sstg_traj_error(const float* pred, const float* tgt, const int32_t* seg_off,
                            static_cast<cudaStream_t>(stream));
 }
 
+int sstg_decode_tracks(const int32_t* start, const int16_t* delta, int32_t total_peds, float* obs_rel,
+                       float* pred_rel, float* last_obs, void* stream) {
+  if (total_peds < 0) return SSTG_EINVAL;
+  if (total_peds == 0) return SSTG_OK;
+  if (!start || !delta || !obs_rel || !pred_rel || !last_obs) return SSTG_EINVAL;
+  if (!aligned16(delta) || !aligned16(obs_rel) || !aligned16(pred_rel)) return SSTG_EINVAL;
+  return launch_decode_tracks(start, delta, total_peds, obs_rel, pred_rel, last_obs,
+                              static_cast<cudaStream_t>(stream));
+}
+
 // ---- training path ------------------------------------------------------------------
 int sstg_train_partial_rows(int32_t S, int32_t n_tiles, int32_t* rows_st, int32_t* rows_tx) {
   if (S < 0 || n_tiles < 0 || !rows_st || !rows_tx) return SSTG_EINVAL;

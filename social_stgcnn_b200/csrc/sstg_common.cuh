@@ -111,6 +111,8 @@ int launch_rel_to_abs(const float* rel, const double* init, const int32_t* seg_o
                       cudaStream_t st);
 int launch_traj_error(const float* pred, const float* tgt, const int32_t* seg_off, int S, int P, int T,
                       double* sum_dist, double* final_dist, cudaStream_t st);
+int launch_decode_tracks(const int32_t* start, const int16_t* delta, int P, float* obs_rel, float* pred_rel,
+                         float* last_obs, cudaStream_t st);
 int txpcnn_tile_width(int max_n);
 int txpcnn_bwd_rows(int n_tiles);
 int launch_txpcnn_backward(const float* dOut, const float* Usave, const float* Xsave, long long layer_stride,

@@ -176,6 +176,12 @@ class TrajectoryDataset(Dataset):
         self.non_linear_ped = f32(np.concatenate(non_linear))
         cum = [0] + np.cumsum(counts).tolist()
         self.seq_start_end = list(zip(cum, cum[1:]))
+        # the same tracks in the 88 B/pedestrian fixed-point host format (None if a step overflows int16)
+        try:
+            from .engine import pack_tracks
+            self.compact = pack_tracks(seq_all) if seq_all.shape[2] == 20 else None
+        except OverflowError:
+            self.compact = None
 
         # ---- graphs: two launches over the packed batch instead of 2 * num_seq Python graph builds
         dev = torch.device(device) if device is not None else _cuda_device()

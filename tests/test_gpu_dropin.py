@@ -262,3 +262,27 @@ def test_driver_fit_writes_reference_artifacts(golden, dev, tmp_path):
     ie = sstg.InferenceEngine.from_state_dict(sd, dev)
     assert abs(driver.validate_epoch(d, ie, 16) - metrics["val_loss"][best]) < 1e-6
     assert int(sd["st_gcns.0.tcn.0.num_batches_tracked"]) == int(golden.weights["eth.nbt"][0]) + 70 * (best + 1)
+
+
+def test_compact_host_format_is_bit_exact(golden, dev):
+    """sstg_decode_tracks rebuilds obs_traj_rel / pred_traj_rel / obs_traj[:, :, -1] of the dataset
+    bit for bit from the 88-byte fixed-point tracks, and the host pipeline fed with them returns
+    exactly what the fp32 interface returns."""
+    import social_stgcnn_b200 as sstg
+    from social_stgcnn_b200.utils import TrajectoryDataset
+    d = TrajectoryDataset(os.path.join(GOLD, "datasets", "eth", "test") + "/", obs_len=8, pred_len=12, skip=1,
+                          norm_lap_matr=True, device=dev)
+    assert d.compact is not None
+    start, delta = (torch.from_numpy(a) for a in d.compact)
+    o, p, l = sstg.decode_tracks(start.to(dev), delta.to(dev))
+    torch.cuda.synchronize()
+    assert torch.equal(o.cpu(), d.obs_traj_rel) and torch.equal(p.cpu(), d.pred_traj_rel)
+    assert torch.equal(l.cpu(), d.obs_traj[:, :, -1])
+    params, bn = golden.params("eth")
+    eng = sstg.InferenceEngine(params, bn, dev)
+    a1, f1 = eng.infer_host(d.plan_obs, d.obs_traj_rel.pin_memory(), d.pred_traj_rel.pin_memory(),
+                            d.obs_traj[:, :, -1].contiguous().pin_memory(), 20, chunk_scenes=16, seed=1)
+    a1, f1 = a1.copy(), f1.copy()
+    a2, f2 = eng.infer_host(d.plan_obs, None, None, None, 20, chunk_scenes=16, seed=1,
+                            compact=(start.pin_memory(), delta.pin_memory()))
+    assert np.array_equal(a1, a2) and np.array_equal(f1, f2)

@@ -104,3 +104,26 @@ def test_batched_poly_fit_equals_scalar():
     got = _poly_fit_batch(seq, 12, 0.002)
     ref = np.array([poly_fit(s, 12, 0.002) for s in seq])
     assert np.array_equal(got, ref) and got[5] == 0.0 and 0 < got.mean() < 1
+
+
+def test_pack_tracks_format_and_overflow(golden):
+    """Compact host format: int32 start + int16 steps (1e-4 units) reproduce the dataset's rounded
+    float64 positions exactly; steps beyond +-3.2767 m are refused (fp32 interface instead)."""
+    import social_stgcnn_b200 as sstg
+    from social_stgcnn_b200.utils import load_scenes
+    seqs, rels, *_ = load_scenes(os.path.join(GOLD, "datasets", "eth", "test") + "/", 8, 12, 1, 0.002, 1, "\t")
+    traj = np.concatenate(seqs)                                       # [181, 2, 20] float64, 4 decimals
+    start, delta = sstg.pack_tracks(traj)
+    assert start.dtype == np.int32 and delta.dtype == np.int16 and delta.shape == (181, 2, 20)
+    assert np.all(delta[:, :, 0] == 0)
+    k = start[:, :, None].astype(np.int64) + np.cumsum(delta.astype(np.int64), axis=2)
+    assert np.array_equal(k / 1e4, traj)                              # what sstg_decode_tracks divides
+    rel = np.zeros_like(traj)
+    rel[:, :, 1:] = (k / 1e4)[:, :, 1:] - (k / 1e4)[:, :, :-1]
+    assert np.array_equal(rel, np.concatenate(rels))
+    bad = traj.copy()
+    bad[0, 0, 5] += 4.0
+    with pytest.raises(OverflowError):
+        sstg.pack_tracks(bad)
+    with pytest.raises(ValueError):
+        sstg.pack_tracks(traj[:, :, :8])
