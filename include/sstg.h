@@ -99,6 +99,16 @@ int sstg_stgcn_forward(const float* V, const float* A, const int32_t* seg_off, c
                        int32_t S, int32_t max_n, const float* params, const float* bn,
                        float* H, int32_t sm_count, void* stream);
 
+/* ---- (1)+(2) fused: graph construction + st_gcn without materialising A ------------------
+ * For a packed evaluation that needs V_pred / ADE / FDE but not the adjacency itself
+ * (test.py's loop): seq_to_graph (utils.py:23-53, fp32 mode, normalised Laplacian) and
+ * st_gcn.forward (model.py:145-155, eval BN) computed straight from the displacements, A kept
+ * in shared memory -- 32 N^2 bytes per scene neither written nor read.  N <= 64 only
+ * (SSTG_ETOOBIG otherwise: use sstg_graph_build + sstg_stgcn_forward).
+ *   rel  [P,2,8] obs_traj_rel;  Pws [P*40] scratch;  H as sstg_stgcn_forward */
+int sstg_stgcn_forward_fused(const float* rel, const int32_t* seg_off, int32_t S, int32_t max_n,
+                             const float* params, const float* bn, float* Pws, float* H, void* stream);
+
 /* ---- (3) TXP-CNN --------------------------------------------------------------------
  * Replaces model.py:187-195: flat view (5,8,N)->(8,5,N), tpcnns[0..3] (3x3, time as
  * channels) with PReLU and residuals, tpcnn_ouput, flat view (12,5,N)->(5,12,N).

@@ -9,8 +9,8 @@ is no CPU fallback.
 from ._lib import LIB_PATH, load as load_library  # noqa: F401
 from .engine import (DevicePlan, InferenceEngine, ScenePlan, TrainEngine, backward,  # noqa: F401
                      bn_running_update, decode_tracks, pack_tracks, forward_train, graph_build, group_weights, nll_backward, nll_forward,
-                     sample_ade_fde, sgd_step, stgcn_forward, txpcnn_forward)
+                     sample_ade_fde, sgd_step, stgcn_forward, stgcn_forward_fused, txpcnn_forward)
 
 __all__ = ["ScenePlan", "DevicePlan", "InferenceEngine", "TrainEngine", "graph_build", "stgcn_forward",
-           "txpcnn_forward", "nll_forward", "sample_ade_fde", "forward_train", "nll_backward", "backward",
+           "stgcn_forward_fused", "txpcnn_forward", "nll_forward", "sample_ade_fde", "forward_train", "nll_backward", "backward",
            "bn_running_update", "sgd_step", "pack_tracks", "decode_tracks", "group_weights", "load_library", "LIB_PATH"]

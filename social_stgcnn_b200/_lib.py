@@ -44,6 +44,7 @@ _SIGS.update({
     "sstg_train_step_workspace": (C.c_int64, [_i32, _i32, _i32, _i64]),
     "sstg_train_step": (C.c_int, [_p, _p, _p, _p, _p, _i32, _i32, _i32, _i32, _i64, _p, _p, _p, _p, _i64, _f32, _f32,
                                   _f64, _i32, _p, _p, _p, _p]),
+    "sstg_stgcn_forward_fused": (C.c_int, [_p, _p, _i32, _i32, _p, _p, _p, _p, _p]),
     "sstg_decode_tracks": (C.c_int, [_p, _p, _i32, _p, _p, _p, _p]),
     "sstg_sgd_step": (C.c_int, [_p, _p, _i32, _f32, _f32, _p, _p]),
 })

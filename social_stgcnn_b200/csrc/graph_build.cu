@@ -44,15 +44,6 @@ __device__ __forceinline__ double weight(float s, double) {
   const double nrm = sqrt(static_cast<double>(s));  // math.sqrt (utils.py:24)
   return nrm == 0.0 ? 0.0 : 1.0 / nrm;              // utils.py:25-27
 }
-__device__ __forceinline__ float rsqrt_fast(float x) {
-  float y;
-  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-// inverse distance from the squared distance; a squared distance below FLT_MIN (only the
-// exact-zero case occurs with real coordinates) is the reference's "distance 0 -> weight 0"
-__device__ __forceinline__ float inv_dist(float sq) { return sq >= 1.17549435e-38f ? rsqrt_fast(sq) : 0.f; }
-
 // fp32 mode: one FMA for the squared distance, one MUFU for the inverse distance
 __device__ __forceinline__ float weight(float s, float) { return inv_dist(s); }
 __device__ __forceinline__ float sqdist_mode(float xh, float yh, float xk, float yk, float) {

@@ -105,6 +105,15 @@ int sstg_stgcn_forward(const float* V, const float* A, const int32_t* seg_off, c
                               static_cast<cudaStream_t>(stream));
 }
 
+int sstg_stgcn_forward_fused(const float* rel, const int32_t* seg_off, int32_t S, int32_t max_n,
+                             const float* params, const float* bn, float* Pws, float* H, void* stream) {
+  if (S < 0 || max_n < 1) return SSTG_EINVAL;
+  if (max_n > 64) return SSTG_ETOOBIG;
+  if (S == 0) return SSTG_OK;
+  if (!rel || !seg_off || !params || !bn || !Pws || !H || !aligned16(rel)) return SSTG_EINVAL;
+  return launch_stgcn_forward_fused(rel, seg_off, S, max_n, params, bn, Pws, H, static_cast<cudaStream_t>(stream));
+}
+
 int sstg_txpcnn_forward(const float* H, const int32_t* seg_off, const int32_t* tile_off, int32_t n_tiles,
                         int32_t max_n, const float* params, float* out, void* stream) {
   if (n_tiles < 0 || max_n < 1) return SSTG_EINVAL;

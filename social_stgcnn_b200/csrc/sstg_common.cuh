@@ -96,6 +96,15 @@ __device__ __forceinline__ void bulk_wait_read() {
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 __device__ __forceinline__ float prelu(float x, float a) { return x >= 0.f ? x : a * x; }
+__device__ __forceinline__ float rsqrt_fast(float x) {
+  float y;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// inverse distance from the squared distance; a squared distance below FLT_MIN (only the
+// exact-zero case occurs with real coordinates) is the reference's "distance 0 -> weight 0"
+__device__ __forceinline__ float inv_dist(float sq) { return sq >= 1.17549435e-38f ? rsqrt_fast(sq) : 0.f; }
+
 #endif  // __CUDACC__
 
 // launchers (one per .cu file)
@@ -111,6 +120,8 @@ int launch_rel_to_abs(const float* rel, const double* init, const int32_t* seg_o
                       cudaStream_t st);
 int launch_traj_error(const float* pred, const float* tgt, const int32_t* seg_off, int S, int P, int T,
                       double* sum_dist, double* final_dist, cudaStream_t st);
+int launch_stgcn_forward_fused(const float* rel, const int32_t* seg_off, int S, int max_n, const float* params,
+                               const float* bn, float* Pws, float* H, cudaStream_t st);
 int launch_decode_tracks(const int32_t* start, const int16_t* delta, int P, float* obs_rel, float* pred_rel,
                          float* last_obs, cudaStream_t st);
 int txpcnn_tile_width(int max_n);

@@ -1,0 +1,286 @@
+// Fused front of the inference pipeline for N <= 64: graph construction AND the st_gcn block in
+// two kernels that never materialise the (8,N,N) adjacency in HBM.
+//
+//   reference: seq_to_graph (utils.py:23-53)  ->  A  ->  st_gcn.forward(v, A) (model.py:145-155)
+//
+// The packed evaluation (test.py's loop) only needs V_pred and the ADE/FDE, not A itself, so
+// writing 32 N^2 bytes per scene and reading them back (the two HBM-bound kernels of the unfused
+// pipeline: 17.2 GB each way for 131,072 64-pedestrian scenes) is avoidable:
+//
+//   kernel F1 (graph_agg_kernel): work item = (scene, 4 timesteps), warp <-> timestep.
+//     pass 1  w_hk = 1/|d_hk| once into a per-warp shared tile, column sums on the fly (exactly the
+//             fast graph kernel), ds = rsqrt(1 + sum), tile diagonal := -(d - 1)
+//     pass 2  y[c,k] = sum_h g[c,h] A[h,k] = -ds_k * sum_h (g[c,h] ds_h) W~[h,k]   (A = -W~ ds ds^T)
+//             with g = 1x1 conv of the displacements (model.py:66), read straight from the tile;
+//             BN1 (eval, folded) + PReLU1 -> P (5,8,N) per scene -- 160 N bytes instead of 32 N^2
+//   kernel F2 (stgcn_tail_kernel): (3,1) temporal conv (+BN2 folded) + residual 1x1 conv (+BN_res
+//             folded) + PReLU2 (model.py:113-125,147-153) -> H (5,8,N), thread per (pedestrian, t).
+//
+// Arithmetic differs from the unfused path only by association (y is formed from w, ds and g
+// without rounding A to fp32 first): ~1e-7 relative, inside the 1e-5 parity bar (tests compare
+// the fused pipeline with the reference's golden V_pred).
+#include "sstg_common.cuh"
+
+namespace sstg {
+
+namespace {
+
+constexpr int U_WARPS = 4;
+constexpr int U_THREADS = U_WARPS * 32;
+
+struct FrontParams {
+  float gw[C][2], gb[C];
+  float s1[C], o1[C], a1;
+};
+struct TailParams {
+  float w2[C][C][3], b2[C];  // BN2 folded in
+  float rw[C][2], rb[C];     // BN_res folded in
+  float a2;
+};
+
+template <int NJ>
+__global__ void __launch_bounds__(U_THREADS)
+graph_agg_kernel(const float* __restrict__ rel, const int32_t* __restrict__ seg_off, int S, int NP, int wtile,
+                 const float* __restrict__ params, const float* __restrict__ bn, float* __restrict__ Pout) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  FrontParams& fp = *reinterpret_cast<FrontParams*>(smem_raw);
+  float* xs = reinterpret_cast<float*>(smem_raw + ((sizeof(FrontParams) + 15) & ~size_t(15)));  // [4][NP]
+  float* ys = xs + U_WARPS * NP;                                                               // [4][NP]
+  float* gsm = ys + U_WARPS * NP + static_cast<size_t>(threadIdx.x >> 5) * NP * 8;             // [warp][NP][8]
+  float* Wt = ys + U_WARPS * NP + U_WARPS * NP * 8 + static_cast<size_t>(threadIdx.x >> 5) * wtile;  // [warp][N*N]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int T = T_OBS, groups = T_OBS / U_WARPS;
+  const long long items = static_cast<long long>(S) * groups;
+
+  if (tid < C) {
+    const int c = tid;
+    fp.gw[c][0] = params[P_GCN_W + 2 * c];
+    fp.gw[c][1] = params[P_GCN_W + 2 * c + 1];
+    fp.gb[c] = params[P_GCN_B + c];
+    const float s1 = params[P_BN1_G + c] / sqrtf(bn[5 + c] + BN_EPS);
+    fp.s1[c] = s1;
+    fp.o1[c] = params[P_BN1_B + c] - bn[c] * s1;
+    if (c == 0) fp.a1 = params[P_PRELU1];
+  }
+
+  long long it = blockIdx.x;
+  int s = 0, t0 = 0, n0 = 0, N = 0;
+  float4 pre = make_float4(0.f, 0.f, 0.f, 0.f);
+  auto fetch = [&](long long item) {
+    s = static_cast<int>(item / groups);
+    t0 = static_cast<int>(item - static_cast<long long>(s) * groups) * U_WARPS;
+    n0 = seg_off[s];
+    N = seg_off[s + 1] - n0;
+    if (tid < 2 * N) pre = *reinterpret_cast<const float4*>(rel + (static_cast<size_t>(n0) * 2 + tid) * T + t0);
+  };
+  if (it < items) fetch(it);
+
+  while (it < items) {
+    const int ct0 = t0, cn0 = n0, cN = N;
+    if (tid < 2 * cN) {
+      float* dst = ((tid & 1) ? ys : xs) + (tid >> 1);
+      dst[0] = pre.x;
+      dst[NP] = pre.y;
+      dst[2 * NP] = pre.z;
+      dst[3 * NP] = pre.w;
+    }
+    __syncthreads();  // also publishes fp on the first trip
+    it += gridDim.x;
+    if (it < items) fetch(it);
+
+    const float* xt = xs + warp * NP;
+    const float* yt = ys + warp * NP;
+    float xk[NJ], yk[NJ], sum[NJ][2];
+    bool kv[NJ];
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+      const int k = lane + 32 * j;
+      kv[j] = k < cN;
+      xk[j] = kv[j] ? xt[k] : 0.f;
+      yk[j] = kv[j] ? yt[k] : 0.f;
+      sum[j][0] = sum[j][1] = 0.f;
+    }
+    // ---- pass 1: inverse distances once, column sums on the fly
+    float* wp = Wt + lane;
+    int h = 0;
+    for (; h + 4 <= cN; h += 4) {
+      const float4 xh = *reinterpret_cast<const float4*>(xt + h);
+      const float4 yh = *reinterpret_cast<const float4*>(yt + h);
+      const float xa[4] = {xh.x, xh.y, xh.z, xh.w}, ya[4] = {yh.x, yh.y, yh.z, yh.w};
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+          const float dx = xa[u] - xk[j], dy = ya[u] - yk[j];
+          const float w = inv_dist(fmaf(dx, dx, dy * dy));
+          sum[j][u & 1] += w;
+          if (kv[j]) wp[32 * j] = w;
+        }
+        wp += cN;
+      }
+    }
+    for (; h < cN; ++h) {
+      const float xh = xt[h], yh = yt[h];
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) {
+        const float dx = xh - xk[j], dy = yh - yk[j];
+        const float w = inv_dist(fmaf(dx, dx, dy * dy));
+        sum[j][0] += w;
+        if (kv[j]) wp[32 * j] = w;
+      }
+      wp += cN;
+    }
+    float dsk[NJ];
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+      const int k = lane + 32 * j;
+      const float lkk = sum[j][0] + sum[j][1];
+      dsk[j] = rsqrt_fast(1.f + lkk);
+      if (kv[j]) {
+        Wt[k * cN + k] = -lkk;  // A = -(W~ ds_h ds_k) uniformly, with W~_kk = -(d_k - 1)
+        // g[c,k] ds_k for the aggregation (1x1 conv of the displacement, model.py:66)
+        float4 g4;
+        g4.x = fmaf(fp.gw[0][1], yk[j], fmaf(fp.gw[0][0], xk[j], fp.gb[0])) * dsk[j];
+        g4.y = fmaf(fp.gw[1][1], yk[j], fmaf(fp.gw[1][0], xk[j], fp.gb[1])) * dsk[j];
+        g4.z = fmaf(fp.gw[2][1], yk[j], fmaf(fp.gw[2][0], xk[j], fp.gb[2])) * dsk[j];
+        g4.w = fmaf(fp.gw[3][1], yk[j], fmaf(fp.gw[3][0], xk[j], fp.gb[3])) * dsk[j];
+        *reinterpret_cast<float4*>(gsm + k * 8) = g4;
+        gsm[k * 8 + 4] = fmaf(fp.gw[4][1], yk[j], fmaf(fp.gw[4][0], xk[j], fp.gb[4])) * dsk[j];
+      }
+    }
+    __syncwarp();
+    // ---- pass 2: acc[c,k] = sum_h (g[c,h] ds_h) W~[h,k]; columns beyond N read slack and are discarded
+    float acc[C][NJ];
+#pragma unroll
+    for (int c = 0; c < C; ++c)
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) acc[c][j] = 0.f;
+    const float* wr = Wt + lane;
+#pragma unroll 4
+    for (int hh = 0; hh < cN; ++hh) {
+      const float4 g4 = *reinterpret_cast<const float4*>(gsm + hh * 8);
+      const float g5 = gsm[hh * 8 + 4];
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) {
+        const float a = wr[32 * j];
+        acc[0][j] = fmaf(g4.x, a, acc[0][j]);
+        acc[1][j] = fmaf(g4.y, a, acc[1][j]);
+        acc[2][j] = fmaf(g4.z, a, acc[2][j]);
+        acc[3][j] = fmaf(g4.w, a, acc[3][j]);
+        acc[4][j] = fmaf(g5, a, acc[4][j]);
+      }
+      wr += cN;
+    }
+    // ---- y = -ds_k acc; BN1 + PReLU1 -> P (5,8,N)
+    float* Ps = Pout + static_cast<size_t>(cn0) * (C * T_OBS) + static_cast<size_t>(ct0 + warp) * cN;
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+      const int k = lane + 32 * j;
+      if (kv[j]) {
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+          const float y = -(dsk[j] * acc[c][j]);
+          Ps[static_cast<size_t>(c) * T_OBS * cN + k] = prelu(fmaf(y, fp.s1[c], fp.o1[c]), fp.a1);
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// H[co,t,n] = PReLU2( b2' + sum_ci sum_kt w2'[co,ci,kt] P[ci,t+kt-1,n] + rw' . v[t,n] + rb' )
+__global__ void __launch_bounds__(256)
+stgcn_tail_kernel(const float* __restrict__ Pin, const float* __restrict__ rel, const int32_t* __restrict__ seg_off,
+                  int S, const float* __restrict__ params, const float* __restrict__ bn, float* __restrict__ H) {
+  __shared__ TailParams tp;
+  const int tid = threadIdx.x;
+  if (tid < C) {
+    const int c = tid;
+    const float s2 = params[P_BN2_G + c] / sqrtf(bn[15 + c] + BN_EPS);
+    for (int ci = 0; ci < C; ++ci)
+      for (int k = 0; k < 3; ++k) tp.w2[c][ci][k] = params[P_TCN_W + (c * C + ci) * 3 + k] * s2;
+    tp.b2[c] = (params[P_TCN_B + c] - bn[10 + c]) * s2 + params[P_BN2_B + c];
+    const float sr = params[P_BNR_G + c] / sqrtf(bn[25 + c] + BN_EPS);
+    tp.rw[c][0] = params[P_RES_W + c * 2 + 0] * sr;
+    tp.rw[c][1] = params[P_RES_W + c * 2 + 1] * sr;
+    tp.rb[c] = (params[P_RES_B + c] - bn[20 + c]) * sr + params[P_BNR_B + c];
+    if (c == 0) tp.a2 = params[P_PRELU2];
+  }
+  __syncthreads();
+  for (int s = blockIdx.x; s < S; s += gridDim.x) {
+    const int n0 = seg_off[s], N = seg_off[s + 1] - n0;
+    const float* Ps = Pin + static_cast<size_t>(n0) * (C * T_OBS);
+    float* Hs = H + static_cast<size_t>(n0) * (C * T_OBS);
+    for (int i = tid; i < T_OBS * N; i += blockDim.x) {  // i = t*N + n: coalesced along the pedestrian axis
+      const int t = i / N, n = i - t * N;
+      float z[C];
+#pragma unroll
+      for (int co = 0; co < C; ++co) z[co] = tp.b2[co];
+#pragma unroll
+      for (int kt = 0; kt < 3; ++kt) {
+        const int tt = t + kt - 1;
+        if (tt >= 0 && tt < T_OBS) {
+#pragma unroll
+          for (int ci = 0; ci < C; ++ci) {
+            const float pv = Ps[(ci * T_OBS + tt) * N + n];
+#pragma unroll
+            for (int co = 0; co < C; ++co) z[co] = fmaf(tp.w2[co][ci][kt], pv, z[co]);
+          }
+        }
+      }
+      const float* r = rel + (static_cast<size_t>(n0 + n) * 2) * T_OBS + t;  // rel[p][c][t]
+      const float vx = r[0], vy = r[T_OBS];
+#pragma unroll
+      for (int co = 0; co < C; ++co) {
+        const float res = fmaf(tp.rw[co][1], vy, fmaf(tp.rw[co][0], vx, tp.rb[co]));
+        Hs[(co * T_OBS + t) * N + n] = prelu(z[co] + res, tp.a2);
+      }
+    }
+  }
+}
+
+template <int NJ>
+int launch_front(const float* rel, const int32_t* seg_off, int S, int max_n, const float* params, const float* bn,
+                 float* Pws, cudaStream_t st) {
+  const int NP = (max_n + 3) & ~3;
+  const int wtile = ((max_n * max_n + 3) & ~3) + 64;  // + slack for the unconditional pass-2 reads
+  const size_t smem = ((sizeof(FrontParams) + 15) & ~size_t(15)) +
+                      sizeof(float) * (static_cast<size_t>(2 * U_WARPS * NP) + static_cast<size_t>(U_WARPS) * NP * 8 +
+                                       static_cast<size_t>(U_WARPS) * wtile);
+  auto kern = graph_agg_kernel<NJ>;
+  if (smem > 48 * 1024)
+    SSTG_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)),
+                  "graph_agg smem attr");
+  int dev = 0, sms = 148, per_sm = 1;
+  SSTG_CUDA_TRY(cudaGetDevice(&dev), "cudaGetDevice");
+  SSTG_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev), "sm count");
+  SSTG_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, U_THREADS, smem), "occupancy");
+  if (per_sm < 1) per_sm = 1;
+  const long long items = static_cast<long long>(S) * (T_OBS / U_WARPS);
+  const long long want = static_cast<long long>(sms) * per_sm;
+  const int grid = static_cast<int>(items < want ? items : want);
+  kern<<<grid, U_THREADS, smem, st>>>(rel, seg_off, S, NP, wtile, params, bn, Pws);
+  SSTG_CUDA_TRY(cudaGetLastError(), "graph_agg launch");
+  return SSTG_OK;
+}
+
+}  // namespace
+
+int launch_stgcn_forward_fused(const float* rel, const int32_t* seg_off, int S, int max_n, const float* params,
+                               const float* bn, float* Pws, float* H, cudaStream_t st) {
+  if (S == 0) return SSTG_OK;
+  if (max_n > 64) return SSTG_ETOOBIG;
+  int rc = max_n <= 32 ? launch_front<1>(rel, seg_off, S, max_n, params, bn, Pws, st)
+                       : launch_front<2>(rel, seg_off, S, max_n, params, bn, Pws, st);
+  if (rc != SSTG_OK) return rc;
+  int dev = 0, sms = 148;
+  SSTG_CUDA_TRY(cudaGetDevice(&dev), "cudaGetDevice");
+  SSTG_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev), "sm count");
+  const long long want = static_cast<long long>(sms) * 8;
+  const int grid = static_cast<int>(S < want ? S : want);
+  stgcn_tail_kernel<<<grid, 256, 0, st>>>(Pws, rel, seg_off, S, params, bn, H);
+  SSTG_CUDA_TRY(cudaGetLastError(), "stgcn_tail launch");
+  return SSTG_OK;
+}
+
+}  // namespace sstg

@@ -152,6 +152,27 @@ def stgcn_forward(dp: DevicePlan, V, A, params, bn, *, H=None, sm_count: int = 0
     return H
 
 
+def stgcn_forward_fused(dp: DevicePlan, obs_rel, params, bn, *, H=None, Pws=None):
+    """seq_to_graph + st_gcn.forward (eval) straight from obs_traj_rel [P,2,8] with the adjacency kept on
+    chip (sstg_stgcn_forward_fused; N <= 64) -> H (5,8,N) blocks."""
+    h, dev = dp.host, dp.device
+    for t, w in ((obs_rel, "obs_rel"), (params, "params"), (bn, "bn")):
+        _need(t, torch.float32, w, dev)
+    if tuple(obs_rel.shape) != (h.P, 2, L.T_OBS):
+        raise ValueError(f"obs_rel must be [{h.P}, 2, {L.T_OBS}]")
+    if h.max_n > 64:
+        raise ValueError("the fused graph + st_gcn path handles scenes of up to 64 pedestrians")
+    if H is None:
+        H = torch.empty(h.P * 40, dtype=torch.float32, device=dev)
+    if Pws is None:
+        Pws = torch.empty(h.P * 40, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        L.check(L.load().sstg_stgcn_forward_fused(_ptr(obs_rel), _ptr(dp.seg_off), h.S, h.max_n, _ptr(params),
+                                                  _ptr(bn), _ptr(Pws), _ptr(H), _stream(dev)),
+                "sstg_stgcn_forward_fused")
+    return H
+
+
 def txpcnn_forward(dp: DevicePlan, H, params, *, out=None):
     """model.py:187-195 for the packed batch -> V_pred (5,12,N) blocks."""
     h, dev = dp.host, dp.device
@@ -284,6 +305,7 @@ class InferenceEngine:
         e.g. the chunks of infer_host -- reuses the memory of a larger one)."""
         need = {"V_obs": (plan.P * L.T_OBS * 2, torch.float32), "A_obs": (plan.a_floats, torch.float32),
                 "V_tr": (plan.P * L.T_PRED * 2, torch.float32), "H": (plan.P * 40, torch.float32),
+                "Pws": (plan.P * 40, torch.float32),
                 "V_pred": (plan.P * 60, torch.float32), "min_ade": (plan.P, torch.float64),
                 "min_fde": (plan.P, torch.float64)}
         key = (plan.S, plan.P, plan.a_floats)
@@ -303,32 +325,40 @@ class InferenceEngine:
 
     def infer(self, plan: ScenePlan, obs_rel, pred_rel, last_obs, K: int = 20, *, eps=None, seed: int = 0,
               graph_fp64: bool = False, fp64_dist: bool = False, want_eps: bool = False, want_pred: bool = False,
-              min_ade=None, min_fde=None, want_vtr: bool = True):
+              min_ade=None, min_fde=None, want_vtr: bool = True, fused: bool = False):
         """Device-resident inputs: obs_rel [P,2,8], pred_rel [P,2,12], last_obs [P,2].
         Returns the workspace dict (views valid until the next call) plus eps / pred_abs."""
         dp = plan.on(self.device)
         ws = self.workspace(plan)
-        graph_build(dp, obs_rel, L.T_OBS, fp64=graph_fp64, V=ws["V_obs"], A=ws["A_obs"])
+        fused = bool(fused) and plan.max_n <= 64 and not graph_fp64
+        if fused:   # graph + st_gcn with the adjacency kept on chip: A_obs / V_obs are NOT produced
+            stgcn_forward_fused(dp, obs_rel, self.params, self.bn, H=ws["H"], Pws=ws["Pws"])
+        else:
+            graph_build(dp, obs_rel, L.T_OBS, fp64=graph_fp64, V=ws["V_obs"], A=ws["A_obs"])
+            stgcn_forward(dp, ws["V_obs"], ws["A_obs"], self.params, self.bn, H=ws["H"])
         if want_vtr:  # the (12,N,2) target blocks (V_tr of the dataset tuple; needed by the NLL, not by ADE/FDE)
             graph_build(dp, pred_rel, L.T_PRED, v_only=True, V=ws["V_tr"])
-        stgcn_forward(dp, ws["V_obs"], ws["A_obs"], self.params, self.bn, H=ws["H"])
         txpcnn_forward(dp, ws["H"], self.params, out=ws["V_pred"])
         r = sample_ade_fde(dp, ws["V_pred"], ws["V_tr"] if want_vtr else pred_rel, last_obs, K, eps=eps, seed=seed,
                            want_eps=want_eps, want_pred=want_pred, fp64_dist=fp64_dist, vtr_is_rel=not want_vtr,
                            min_ade=ws["min_ade"] if min_ade is None else min_ade,
                            min_fde=ws["min_fde"] if min_fde is None else min_fde)
         out = dict(ws)
+        if fused:
+            out["A_obs"] = out["V_obs"] = None
         out["min_ade"], out["min_fde"] = r["min_ade"], r["min_fde"]
         out["eps"], out["pred_abs"] = r["eps"], r["pred_abs"]
         return out
 
     def infer_host(self, plan: ScenePlan, obs_rel, pred_rel, last_obs, K: int = 20, *, chunk_scenes: int = 8192,
-                   seed: int = 0, compact=None, **kw):
+                   seed: int = 0, compact=None, fused: bool = True, **kw):
         """End-to-end call with HOST buffers (numpy or CPU tensors, ideally pinned): the batch is
         cut into chunks of `chunk_scenes` scenes and software-pipelined over three streams --
         H2D of chunk i+1 (copy stream) overlaps the kernels of chunk i (current stream) and the
         D2H of chunk i-1's per-pedestrian minima (second copy stream).  PCIe carries 168 B per
         pedestrian in and 16 B out, so the steady state is max(H2D time, kernel time).
+        Only the per-pedestrian minima leave the device, so by default (`fused`) graph build and
+        st_gcn run as the fused pair that keeps the adjacency on chip (scenes of <= 64 pedestrians).
         `compact=(start, delta)` (pack_tracks) replaces the three fp32 host tensors by the 88 B per
         pedestrian fixed-point format, decoded bit-exactly on the device (sstg_decode_tracks).
         Returns (min_ade, min_fde) as numpy float64 arrays of length P (pinned, reused)."""
@@ -381,6 +411,7 @@ class InferenceEngine:
                 decode_tracks(b["start"][:n], b["delta"][:n], obs_rel=b["obs"][:n], pred_rel=b["pred"][:n],
                               last_obs=b["last"][:n])
             self.infer(sub, b["obs"][:n], b["pred"][:n], b["last"][:n], K, seed=seed + 0x9E3779B1 * i, want_vtr=False,
+                       fused=fused,
                        min_ade=st["d_out"][0][p_lo:p_hi], min_fde=st["d_out"][1][p_lo:p_hi], **kw)
             st["free"][i & 1].record(main)
             s_d2h.wait_event(st["free"][i & 1])

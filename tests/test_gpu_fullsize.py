@@ -107,8 +107,16 @@ def test_dense_crowds_properties(golden, dev):
     assert float((r10["min_ade"] - ade20).max()) > 0.0
     # the chunked host pipeline reproduces one-shot runs of the same chunks (seed + 0x9E3779B1 * chunk)
     a_h, f_h = eng.infer_host(plan, torch.from_numpy(obs_rel).pin_memory(), torch.from_numpy(pred_rel).pin_memory(),
-                              torch.from_numpy(last).pin_memory(), 20, chunk_scenes=S, seed=9)
+                              torch.from_numpy(last).pin_memory(), 20, chunk_scenes=S, seed=9, fused=False)
     assert np.array_equal(a_h, ade20.cpu().numpy()) and np.array_equal(f_h, fde20.cpu().numpy())
+    # ... and the fused front (adjacency kept on chip) moves no per-pedestrian minimum by more than 1e-5 of
+    # the position scale: ADE/FDE are continuous in V_pred, and V_pred changes by rounding only
+    rfu = eng.infer(plan, obs, pred, lst, K=20, seed=9, fused=True)
+    torch.cuda.synchronize()
+    assert rfu["A_obs"] is None
+    scale = float(np.abs(obs_abs).max())
+    assert float((rfu["min_ade"] - ade20).abs().max()) < 1e-5 * scale
+    assert float((rfu["min_fde"] - fde20).abs().max()) < 1e-5 * scale
     # oracle spot checks in exact mode, replaying the kernel's own noise
     rx = eng.infer(plan, obs, pred, lst, K=20, seed=9, graph_fp64=True, fp64_dist=True, want_eps=True)
     torch.cuda.synchronize()

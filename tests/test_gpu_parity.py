@@ -263,13 +263,40 @@ def test_infer_host_pipelined_chunks_equal_direct_calls(golden, batch, dev):
     obs_h = batch["obs_rel"].cpu().pin_memory()
     pred_h = batch["pred_rel"].cpu().pin_memory()
     last_h = batch["last_obs"].cpu().pin_memory()
-    for chunk in (7, 32, 10 ** 6):
-        a_h, f_h = eng.infer_host(plan, obs_h, pred_h, last_h, 20, chunk_scenes=chunk, seed=5)
+    for chunk, fused in ((7, True), (32, False), (10 ** 6, True)):
+        a_h, f_h = eng.infer_host(plan, obs_h, pred_h, last_h, 20, chunk_scenes=chunk, seed=5, fused=fused)
         a_h, f_h = a_h.copy(), f_h.copy()
         for i, (lo, hi, p_lo, p_hi, sub) in enumerate(plan.chunks(chunk)):
             r = eng.infer(sub, batch["obs_rel"][p_lo:p_hi].contiguous(), batch["pred_rel"][p_lo:p_hi].contiguous(),
-                          batch["last_obs"][p_lo:p_hi].contiguous(), 20, seed=5 + 0x9E3779B1 * i)
+                          batch["last_obs"][p_lo:p_hi].contiguous(), 20, seed=5 + 0x9E3779B1 * i, fused=fused)
             torch.cuda.synchronize()
             assert np.array_equal(a_h[p_lo:p_hi], r["min_ade"].cpu().numpy()), (chunk, i)
             assert np.array_equal(f_h[p_lo:p_hi], r["min_fde"].cpu().numpy()), (chunk, i)
     assert len(plan.chunks(7)) == (plan.S + 6) // 7
+
+
+@pytest.mark.parametrize("ckpt", ["eth", "zara1"])
+def test_fused_graph_stgcn_front(golden, batch, dev, ckpt):
+    """sstg_stgcn_forward_fused (graph + st_gcn with the adjacency kept in shared memory) against
+    the unfused pair on the same inputs and, through the TXP-CNN, against the reference's V_pred."""
+    import social_stgcnn_b200 as sstg
+    plan, dp = batch["plan"], batch["dp"]
+    params, bn = golden.params(ckpt)
+    p, b = torch.from_numpy(params).to(dev), torch.from_numpy(bn).to(dev)
+    V, A = sstg.graph_build(dp, batch["obs_rel"], 8, fp64=True)
+    H_ref = sstg.stgcn_forward(dp, V, A, p, b)
+    H = sstg.stgcn_forward_fused(dp, batch["obs_rel"], p, b)
+    out = sstg.txpcnn_forward(dp, H, p)
+    torch.cuda.synchronize()
+    H, H_ref, out = H.cpu().numpy(), H_ref.cpu().numpy(), out.cpu().numpy()
+    worst_h = worst = 0.0
+    for i, name in enumerate(batch["names"]):
+        n, o = int(plan.n_peds[i]), int(plan.seg_off[i])
+        worst_h = max(worst_h, rel_err(H[o * 40:(o + n) * 40], H_ref[o * 40:(o + n) * 40]))
+        got = out[o * 60:(o + n) * 60].reshape(1, 5, 12, n)
+        worst = max(worst, rel_err(got, golden.fwd[f"{ckpt}.{name}.eval"]))
+    assert worst_h < TOL, worst_h
+    assert worst < TOL, worst
+    big = sstg.ScenePlan([65, 3])
+    with pytest.raises(ValueError):
+        sstg.stgcn_forward_fused(big.on(dev), torch.zeros(68, 2, 8, device=dev), p, b)
