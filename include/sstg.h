@@ -40,6 +40,7 @@ extern "C" {
 #define SSTG_MAX_PEDS 256  /* largest scene the kernels accept (shared-memory bound) */
 #define SSTG_XTILE_COLS 128 /* TXP-CNN tile: whole scenes up to this many pedestrian columns */
 #define SSTG_XTILE_MAX_SCENES 32
+#define SSTG_XTILE_MAX_PAIRS 64  /* a tile holds at most 64 column pairs: sum over its scenes of ceil(N_s / 2) */
 #define SSTG_ST_PARAMS 142          /* st_gcn parameters: the first 142 floats of the block */
 #define SSTG_TXP_GRAD_STRIDE 7424   /* row length of the TXP-CNN partial-gradient buffer (7421 padded) */
 #define SSTG_SAVE_FLOATS_PER_PED 600 /* activations kept for backward: Y 40, Z 40, H 40, U 4x60, X 4x60 */
@@ -67,14 +68,15 @@ const char* sstg_last_cuda_error(void);
 /* ---- host-side planning (pure CPU, no CUDA) ---------------------------------------
  * From the per-scene pedestrian counts compute the packed-batch offsets and the
  * TXP-CNN tile table (whole scenes per tile; at most SSTG_XTILE_COLS columns and
- * SSTG_XTILE_MAX_SCENES scenes, narrower -- down to 8 columns -- for batches too small to
+ * SSTG_XTILE_MAX_SCENES scenes and SSTG_XTILE_MAX_PAIRS column pairs, narrower -- down to 8 columns -- for batches too small to
  * fill the GPU with full tiles: cap = clamp(ceil(P / 296), 8, 128)).  seg_off_host[S+1], a_off_host[S+1], tile_off_host[S+1] are
  * caller-provided; tile t covers scenes [tile_off[t], tile_off[t+1]).
- * Outputs *n_tiles, *max_n, *a_floats (total floats of the packed A buffer, padded).
+ * Outputs *n_tiles, *max_n, *a_floats (total floats of the packed A buffer, padded) and
+ * *tile_cols (may be NULL): shared-memory columns of the widest tile, for sstg_txpcnn_forward.
  * Replaces the `seq_start_end` bookkeeping of TrajectoryDataset (utils.py:186-190). */
 int sstg_plan_host(const int32_t* n_peds_host, int32_t S, int32_t T,
                    int32_t* seg_off_host, int64_t* a_off_host, int32_t* tile_off_host,
-                   int32_t* n_tiles, int32_t* max_n, int64_t* a_floats);
+                   int32_t* n_tiles, int32_t* max_n, int64_t* a_floats, int32_t* tile_cols);
 
 /* ---- (1) graph construction --------------------------------------------------------
  * Replaces utils.seq_to_graph + anorm (utils.py:23-53) incl. the networkx
@@ -115,9 +117,12 @@ int sstg_stgcn_forward_fused(const float* rel, const int32_t* seg_off, int32_t S
  *   H    as written by sstg_stgcn_forward
  *   out  scene s at float offset seg_off[s]*60, layout (5,12,N_s) == V_pred[0] of
  *        social_stgcnn.forward (model.py:198)
- *   tile_off [n_tiles+1] from sstg_plan_host (device copy). */
+ *   tile_off [n_tiles+1] from sstg_plan_host (device copy); tile_cols from sstg_plan_host
+ *   (0 = unknown: the kernel then reserves shared memory for the widest possible tile).
+ * Scenes of up to 128 pedestrians run the Winograd F(2,3) kernel (txpcnn_wino.cu), larger
+ * ones and the training forward the direct FFMA2 kernel (txpcnn_fwd.cu). */
 int sstg_txpcnn_forward(const float* H, const int32_t* seg_off, const int32_t* tile_off,
-                        int32_t n_tiles, int32_t max_n, const float* params,
+                        int32_t n_tiles, int32_t max_n, int32_t tile_cols, const float* params,
                         float* out, void* stream);
 
 /* ---- (4a) bivariate Gaussian NLL, forward -------------------------------------------

@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_PKG, "libsstg.so")
 
 T_OBS, T_PRED, C_IN, C_OUT = 8, 12, 2, 5
 N_PARAMS, N_BN, MAX_PEDS = 7563, 30, 256
-XTILE_COLS, XTILE_MAX_SCENES = 128, 32
+XTILE_COLS, XTILE_MAX_SCENES, XTILE_MAX_PAIRS = 128, 32, 64
 ST_PARAMS, TXP_GRAD_STRIDE, SAVE_FLOATS_PER_PED = 142, 7424, 600
 GRAPH_NORM_LAP, GRAPH_FP64, GRAPH_V_ONLY = 1, 2, 4
 EVAL_FP64_DIST, EVAL_VTR_IS_REL = 1, 2
@@ -25,10 +25,10 @@ _SIGS = {
     "sstg_version": (C.c_int, []),
     "sstg_error_string": (C.c_char_p, [C.c_int]),
     "sstg_last_cuda_error": (C.c_char_p, []),
-    "sstg_plan_host": (C.c_int, [_p, _i32, _i32, _p, _p, _p, _p, _p, _p]),
+    "sstg_plan_host": (C.c_int, [_p, _i32, _i32, _p, _p, _p, _p, _p, _p, _p]),
     "sstg_graph_build": (C.c_int, [_p, _p, _p, _i32, _i32, _i32, _p, _p, _i32, _p]),
     "sstg_stgcn_forward": (C.c_int, [_p, _p, _p, _p, _i32, _i32, _p, _p, _p, _i32, _p]),
-    "sstg_txpcnn_forward": (C.c_int, [_p, _p, _p, _i32, _i32, _p, _p, _p]),
+    "sstg_txpcnn_forward": (C.c_int, [_p, _p, _p, _i32, _i32, _i32, _p, _p, _p]),
     "sstg_nll_forward": (C.c_int, [_p, _p, _p, _i32, _p, _p]),
     "sstg_sample_ade_fde": (C.c_int, [_p, _p, _p, _p, _i32, _i32, _i32, _p, _u64, _p, _p, _p, _p, _i32, _p]),
 }

@@ -39,7 +39,8 @@ const char* sstg_error_string(int code) {
 const char* sstg_last_cuda_error(void) { return g_last_cuda_error; }
 
 int sstg_plan_host(const int32_t* n_peds_host, int32_t S, int32_t T, int32_t* seg_off_host, int64_t* a_off_host,
-                   int32_t* tile_off_host, int32_t* n_tiles, int32_t* max_n, int64_t* a_floats) {
+                   int32_t* tile_off_host, int32_t* n_tiles, int32_t* max_n, int64_t* a_floats,
+                   int32_t* tile_cols) {
   if (S < 0 || T <= 0 || (S > 0 && !n_peds_host) || !seg_off_host || !a_off_host || !tile_off_host || !n_tiles ||
       !max_n || !a_floats)
     return SSTG_EINVAL;
@@ -51,7 +52,8 @@ int sstg_plan_host(const int32_t* n_peds_host, int32_t S, int32_t T, int32_t* se
   int64_t cap64 = (total + 295) / 296;
   const int32_t cap = static_cast<int32_t>(cap64 < 8 ? 8 : (cap64 > SSTG_XTILE_COLS ? SSTG_XTILE_COLS : cap64));
   int64_t ped = 0, af = 0;
-  int32_t mx = 0, nt = 0, cols = 0, scenes = 0;
+  int32_t mx = 0, nt = 0, cols = 0, scenes = 0, pairs = 0;
+  int32_t wcol = 1, wmax = 0;  // shared-memory columns of the current tile in the odd-start layout of txpcnn_wino.cu
   seg_off_host[0] = 0;
   a_off_host[0] = 0;
   tile_off_host[0] = 0;
@@ -61,12 +63,19 @@ int sstg_plan_host(const int32_t* n_peds_host, int32_t S, int32_t T, int32_t* se
     if (n > SSTG_MAX_PEDS) return SSTG_ETOOBIG;
     if (n > mx) mx = n;
     // close the current TXP-CNN tile if this scene does not fit any more
-    if (scenes > 0 && (cols + n > cap || scenes == SSTG_XTILE_MAX_SCENES)) {
+    if (scenes > 0 && (cols + n > cap || scenes == SSTG_XTILE_MAX_SCENES ||
+                       pairs + ((n + 1) >> 1) > SSTG_XTILE_MAX_PAIRS)) {
       tile_off_host[++nt] = s;
       cols = 0;
       scenes = 0;
+      pairs = 0;
+      wcol = 1;
     }
     cols += n;
+    pairs += (n + 1) >> 1;
+    wcol += n + 1;
+    wcol += (~wcol) & 1;  // the next scene starts at an odd column
+    if (wcol + 1 > wmax) wmax = wcol + 1;
     ++scenes;
     ped += n;
     if (ped > INT32_MAX / 64) return SSTG_ETOOBIG;  // int32 element offsets inside the kernels
@@ -79,6 +88,7 @@ int sstg_plan_host(const int32_t* n_peds_host, int32_t S, int32_t T, int32_t* se
   *n_tiles = nt;
   *max_n = mx;
   *a_floats = af;
+  if (tile_cols) *tile_cols = wmax;
   return SSTG_OK;
 }
 
@@ -115,12 +125,12 @@ int sstg_stgcn_forward_fused(const float* rel, const int32_t* seg_off, int32_t S
 }
 
 int sstg_txpcnn_forward(const float* H, const int32_t* seg_off, const int32_t* tile_off, int32_t n_tiles,
-                        int32_t max_n, const float* params, float* out, void* stream) {
+                        int32_t max_n, int32_t tile_cols, const float* params, float* out, void* stream) {
   if (n_tiles < 0 || max_n < 1) return SSTG_EINVAL;
   if (max_n > SSTG_MAX_PEDS) return SSTG_ETOOBIG;
   if (n_tiles == 0) return SSTG_OK;
   if (!H || !seg_off || !tile_off || !params || !out) return SSTG_EINVAL;
-  return launch_txpcnn_forward(H, seg_off, tile_off, n_tiles, max_n, params, out, nullptr, nullptr, 0,
+  return launch_txpcnn_forward(H, seg_off, tile_off, n_tiles, max_n, params, out, nullptr, nullptr, 0, tile_cols,
                                static_cast<cudaStream_t>(stream));
 }
 
@@ -194,7 +204,7 @@ int sstg_forward_train(const float* V, const float* A, const int32_t* seg_off, c
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   int rc = launch_stgcn_train_forward(V, A, seg_off, a_off, S, max_n, params, Y, Z, H, scene_stats, st);
   if (rc != SSTG_OK) return rc;
-  return launch_txpcnn_forward(H, seg_off, tile_off, n_tiles, max_n, params, Vpred, U, X, P * 60, st);
+  return launch_txpcnn_forward(H, seg_off, tile_off, n_tiles, max_n, params, Vpred, U, X, P * 60, 0, st);
 }
 
 int sstg_bn_running_update(const float* scene_stats, const int32_t* seg_off, int32_t S, double momentum,

@@ -115,7 +115,7 @@ int launch_stgcn_forward(const float* V, const float* A, const int32_t* seg_off,
                          cudaStream_t st);
 int launch_txpcnn_forward(const float* H, const int32_t* seg_off, const int32_t* tile_off, int n_tiles, int max_n,
                           const float* params, float* out, float* Usave, float* Xsave, long long layer_stride,
-                          cudaStream_t st);
+                          int tile_cols, cudaStream_t st);
 int launch_rel_to_abs(const float* rel, const double* init, const int32_t* seg_off, int S, int P, int T, float* out,
                       cudaStream_t st);
 int launch_traj_error(const float* pred, const float* tgt, const int32_t* seg_off, int S, int P, int T,
@@ -125,6 +125,9 @@ int launch_stgcn_forward_fused(const float* rel, const int32_t* seg_off, int S, 
 int launch_decode_tracks(const int32_t* start, const int16_t* delta, int P, float* obs_rel, float* pred_rel,
                          float* last_obs, cudaStream_t st);
 int txpcnn_tile_width(int max_n);
+int txpcnn_wino_mode();
+int launch_txpcnn_forward_wino(const float* H, const int32_t* seg_off, const int32_t* tile_off, int n_tiles,
+                               const float* params, float* out, int mode, int tile_cols_hint, cudaStream_t st);
 int txpcnn_bwd_rows(int n_tiles);
 int launch_txpcnn_backward(const float* dOut, const float* Usave, const float* Xsave, long long layer_stride,
                            const float* H, const int32_t* seg_off, const int32_t* tile_off, int n_tiles, int max_n,

@@ -203,8 +203,14 @@ int txpcnn_tile_width(int max_n) {
 
 int launch_txpcnn_forward(const float* H, const int32_t* seg_off, const int32_t* tile_off, int n_tiles, int max_n,
                           const float* params, float* out, float* Usave, float* Xsave, long long layer_stride,
-                          cudaStream_t st) {
+                          int tile_cols, cudaStream_t st) {
   if (n_tiles == 0) return SSTG_OK;
+  const bool save = Usave != nullptr && Xsave != nullptr;
+  // inference on scenes of up to 128 pedestrians: the Winograd F(2,3) kernel (txpcnn_wino.cu)
+  if (!save && max_n <= X_COLS) {
+    const int mode = txpcnn_wino_mode();
+    if (mode != 0) return launch_txpcnn_forward_wino(H, seg_off, tile_off, n_tiles, params, out, mode, tile_cols, st);
+  }
   // widest tile: up to X_COLS columns of up to MAX_SCENES scenes, or one big scene;
   // one zero separator column before every scene and one after the last
   const int Wp = txpcnn_tile_width(max_n);
@@ -224,7 +230,6 @@ int launch_txpcnn_forward(const float* H, const int32_t* seg_off, const int32_t*
     SSTG_CUDA_TRY(cudaGetLastError(), "txpcnn launch");
     return SSTG_OK;
   };
-  const bool save = Usave != nullptr && Xsave != nullptr;
   if (max_n > X_COLS) return save ? launch(txpcnn_fwd_kernel<2, true>) : launch(txpcnn_fwd_kernel<2, false>);
   return save ? launch(txpcnn_fwd_kernel<1, true>) : launch(txpcnn_fwd_kernel<1, false>);
 }

@@ -48,12 +48,12 @@ class ScenePlan:
         self.seg_off = np.zeros(S + 1, np.int32)
         self.a_off = np.zeros(S + 1, np.int64)
         self.tile_off = np.zeros(S + 1, np.int32)
-        nt, mx, af = np.zeros(1, np.int32), np.zeros(1, np.int32), np.zeros(1, np.int64)
+        nt, mx, af, tc = np.zeros(1, np.int32), np.zeros(1, np.int32), np.zeros(1, np.int64), np.zeros(1, np.int32)
         lib = L.load()
         L.check(lib.sstg_plan_host(n.ctypes.data, S, self.T, self.seg_off.ctypes.data, self.a_off.ctypes.data,
-                                   self.tile_off.ctypes.data, nt.ctypes.data, mx.ctypes.data, af.ctypes.data),
-                "sstg_plan_host")
-        self.n_tiles, self.max_n, self.a_floats = int(nt[0]), int(mx[0]), int(af[0])
+                                   self.tile_off.ctypes.data, nt.ctypes.data, mx.ctypes.data, af.ctypes.data,
+                                   tc.ctypes.data), "sstg_plan_host")
+        self.n_tiles, self.max_n, self.a_floats, self.tile_cols = int(nt[0]), int(mx[0]), int(af[0]), int(tc[0])
         self.tile_off = self.tile_off[: self.n_tiles + 1].copy()
         self.P = int(self.seg_off[-1])
         self._dev: Dict[torch.device, "DevicePlan"] = {}
@@ -182,7 +182,8 @@ def txpcnn_forward(dp: DevicePlan, H, params, *, out=None):
         out = torch.empty(h.P * 60, dtype=torch.float32, device=dev)
     with torch.cuda.device(dev):
         L.check(L.load().sstg_txpcnn_forward(_ptr(H), _ptr(dp.seg_off), _ptr(dp.tile_off), h.n_tiles, h.max_n,
-                                             _ptr(params), _ptr(out), _stream(dev)), "sstg_txpcnn_forward")
+                                             h.tile_cols, _ptr(params), _ptr(out), _stream(dev)),
+                "sstg_txpcnn_forward")
     return out
 
 

@@ -84,7 +84,7 @@ def test_null_and_range_errors_return_codes(lib):
     assert lib.sstg_graph_build(z, z, z, 1, 8, 1000, z, z, 1, z) == -2          # scene too big
     assert lib.sstg_graph_build(z, z, z, 0, 8, 4, z, z, 1, z) == 0              # empty batch is a no-op
     assert lib.sstg_stgcn_forward(z, z, z, z, 1, 4, z, z, z, 0, z) == -1
-    assert lib.sstg_txpcnn_forward(z, z, z, 0, 4, z, z, z) == 0
+    assert lib.sstg_txpcnn_forward(z, z, z, 0, 4, 0, z, z, z) == 0
     assert lib.sstg_sample_ade_fde(z, z, z, z, 1, 4, 0, z, 0, z, z, z, z, 0, z) == -1   # K < 1
     assert lib.sstg_error_string(-2).decode().startswith("scene larger")
 
