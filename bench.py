@@ -274,6 +274,9 @@ def run_ours(args):
         raise RuntimeError("bench.py needs a CUDA device; there is no CPU fallback for the product path")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # NCCL's banner / logs off stdout: rank 0 prints ONE JSON line
+    from social_stgcnn_b200.parallel import bind_process_to_gpu_numa
+    numa_node = bind_process_to_gpu_numa(local)   # before any pinned allocation: first touch lands next to the GPU
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     S, N = args.scenes_per_gpu, N_PEDS
@@ -415,7 +418,8 @@ def run_ours(args):
                                    f"eth checkpoint weights",
                        "scenes_per_gpu": S, "peds_per_scene": N, "ksteps": K_SAMPLES, "graph_mode": "fp32",
                        "l2_policy": "inputs larger than L2 (A is %.1f GB per step)" % (plan.a_floats * 4 / 1e9),
-                       "parallelism": f"scene-sharded x{world}, no data-path collective"},
+                       "parallelism": f"scene-sharded x{world}, no data-path collective",
+                       "numa_node_rank0": numa_node},
             "roofline": {"kernel": "stgcn_fwd_kernel", "bound": "hbm", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak,
                          "traffic": (tr["dram_bytes"] * S / tr["scenes"] if (tr := profiled_traffic()) else None),

@@ -6,11 +6,12 @@ sees one scene at a time), therefore:
   * inference / evaluation needs NO data-path collective -- each rank runs the whole pipeline
     on its shard; the dataset-level ADE/FDE (test.py:125-126: mean over ALL pedestrians) is one
     3-element all-reduce of (sum min-ADE, sum min-FDE, pedestrians);
-  * training needs ONE all-reduce (sum) of the flat 7,563-float gradient per optimiser group
-    (the loss weights 1/batch_size and "last scene unscored" are applied locally, so the sum of
-    the rank gradients IS the group gradient), plus an all-gather of the per-scene BatchNorm
-    statistics (30 floats per scene) so every rank applies the running-statistics recurrence
-    in the global scene order and all replicas stay bit-identical.
+  * training needs ONE all-reduce (sum) per optimiser group over a flat buffer that carries the
+    7,563-float gradient (the loss weights 1/batch_size and "last scene unscored" are applied
+    locally, so the sum of the rank gradients IS the group gradient), the group loss, and the
+    per-scene BatchNorm statistics (30 floats per scene, each rank filling only its own rows, so
+    the sum is the concatenation): every rank then applies the running-statistics recurrence in
+    the global scene order and all replicas stay bit-identical.
 The collectives are torch.distributed calls (plumbing); the arithmetic before and after them
 is libsstg.so.  The helpers below take any process group, so the host logic is tested with
 gloo on CPU tensors (tests/test_parallel_gloo.py) and runs unchanged over NCCL.
@@ -103,6 +104,31 @@ def gather_scene_stats(stats_local: torch.Tensor, counts: Sequence[int], group=N
     return torch.cat([o[:c] for o, c in zip(out, counts)], dim=0)
 
 
+def bind_process_to_gpu_numa(device_index: int) -> Optional[int]:
+    """Pin this process to the CPUs of the NUMA node its GPU hangs off (read from sysfs), BEFORE the
+    pinned host buffers are allocated, so that first-touch places them next to the GPU's PCIe root
+    and host->device copies of all ranks do not cross the socket interconnect.  Returns the node, or
+    None when the topology is not exposed (then nothing changes)."""
+    import os
+    try:
+        pr = torch.cuda.get_device_properties(device_index)
+        bdf = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read().strip())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = cpus & os.sched_getaffinity(0)
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return node
+    except Exception:
+        return None
+
+
 class ShardedEvaluator:
     """test.py's evaluation over a scene-sharded dataset: this rank's InferenceEngine on this
     rank's shard, then the 3-element score reduction."""
@@ -136,6 +162,7 @@ class DistributedTrainer:
 
     def __init__(self, engine, group=None):
         self.engine, self.group = engine, group
+        self._flat = {}
 
     def step(self, n_peds, obs_rel, pred_rel, batch_size: int, lr: float, clip_grad: Optional[float] = None,
              presliced: bool = False):
@@ -161,10 +188,26 @@ class DistributedTrainer:
         else:
             eng.grad.zero_()
             stats = torch.zeros(0, L.N_BN, dtype=torch.float32, device=dev)
-        allreduce_gradient(eng.grad, self.group)
+        # ONE collective per optimiser group: [gradient 7563 | group loss 1 | per-scene BN statistics S x 30]
+        # in a single flat buffer, all-reduced (sum).  Every rank fills only its own scenes' rows of the
+        # statistics block, so the sum IS the concatenation in global scene order.
+        S_all = int(n_peds.size)
         if world > 1:
-            dist.all_reduce(loss_local, op=dist.ReduceOp.SUM, group=self.group)
-        stats_all = gather_scene_stats(stats, [b - a for a, b in bounds], self.group)
+            flat = self._flat.get(S_all)
+            if flat is None:
+                flat = self._flat[S_all] = torch.empty(L.N_PARAMS + 1 + S_all * L.N_BN, dtype=torch.float32, device=dev)
+            flat[:L.N_PARAMS].copy_(eng.grad)
+            flat[L.N_PARAMS] = loss_local[0].float()
+            st = flat[L.N_PARAMS + 1:].view(S_all, L.N_BN)
+            st.zero_()
+            if hi > lo:
+                st[lo:hi].copy_(stats)
+            dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
+            eng.grad.copy_(flat[:L.N_PARAMS])
+            loss_local = flat[L.N_PARAMS:L.N_PARAMS + 1].double()
+            stats_all = st
+        else:
+            stats_all = stats
         full = E.ScenePlan(n_peds)
         E.bn_running_update(full.on(dev), stats_all.contiguous(), eng.bn)
         eng.num_batches_tracked += int(n_peds.size)
