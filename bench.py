@@ -274,7 +274,11 @@ def run_ours(args):
         raise RuntimeError("bench.py needs a CUDA device; there is no CPU fallback for the product path")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # NCCL's banner / logs off stdout: rank 0 prints ONE JSON line
+    # rank 0's stdout is ONE JSON line: the image exports NCCL_DEBUG=VERSION, whose only effect is a banner on
+    # stdout (NCCL ignores NCCL_DEBUG_FILE at that level); higher levels are sent to stderr instead
+    if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+        os.environ.pop("NCCL_DEBUG")
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     from social_stgcnn_b200.parallel import bind_process_to_gpu_numa
     numa_node = bind_process_to_gpu_numa(local)   # before any pinned allocation: first touch lands next to the GPU
     if world > 1:
