@@ -201,6 +201,43 @@ def run_reference(args):
 
 
 # ---------------------------------------------------------------------------------
+# graph-construction leg (BASELINE.json config 5): seq_to_graph on packed tiny scenes
+# ---------------------------------------------------------------------------------
+def run_graph_leg(dev, steps=5, num_scenes=262144):
+    """scenes/s of TrajectoryDataset's graph construction (utils.py:201-211: seq_to_graph of the
+    observed half, T = 8, AND of the predicted half, T = 12, normalised Laplacian) on packed ragged
+    scenes shaped like the nuScenes-mini / ETH-UCY windows (2..5 pedestrians), in the fp64-island
+    mode that is bit-identical to networkx, and in the fp32 mode."""
+    import torch
+    import social_stgcnn_b200 as sstg
+    from social_stgcnn_b200 import engine as E
+    rng = np.random.default_rng(5)
+    n = rng.integers(2, 6, num_scenes).astype(np.int32)
+    obs, pred, _ = synth_batch(int(n.sum()), 1, 99)
+    obs, pred = obs.to(dev), pred.to(dev)
+    p8, p12 = sstg.ScenePlan(n, T=8), sstg.ScenePlan(n, T=12)
+    d8, d12 = p8.on(dev), p12.on(dev)
+    V8 = torch.empty(p8.P * 16, device=dev); A8 = torch.empty(p8.a_floats, device=dev)
+    V12 = torch.empty(p12.P * 24, device=dev); A12 = torch.empty(p12.a_floats, device=dev)
+    out = {"scenes": num_scenes, "peds_per_scene": "2..5", "what": "seq_to_graph of both halves (T=8 and T=12) per scene"}
+    for mode, fp64 in (("fp64_exact", True), ("fp32", False)):
+        def one():
+            E.graph_build(d8, obs, 8, fp64=fp64, V=V8, A=A8)
+            E.graph_build(d12, pred, 12, fp64=fp64, V=V12, A=A12)
+        for _ in range(3):
+            one()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            one()
+        e1.record()
+        torch.cuda.synchronize()
+        out[mode + "_scenes_per_s"] = num_scenes * steps / (e0.elapsed_time(e1) * 1e-3)
+    return out
+
+
+# ---------------------------------------------------------------------------------
 # training leg (BASELINE.json config 2): optimiser groups of 128 ragged scenes
 # ---------------------------------------------------------------------------------
 def synth_ragged_counts(num_scenes, seed):
@@ -389,9 +426,11 @@ def run_ours(args):
     c1.record()
     torch.cuda.synchronize()
     h2d_gbs = (obs_h.numel() + pred_h.numel()) * 4 / (c0.elapsed_time(c1) * 1e-3) / 1e9
-    train = None
+    train = graph_leg = None
     if not args.no_train:
         train = run_train_leg(dev, world, rank, steps=max(20, 10 * args.steps), warmup=5)
+        if rank == 0:
+            graph_leg = run_graph_leg(dev)
 
     t = torch.tensor([ms_total, ms_e2e, ms_e2e_c, ms_fused], dtype=torch.float64, device=dev)
     red = torch.tensor([sum_a, sum_f, float(plan.P)], dtype=torch.float64, device=dev)
@@ -449,6 +488,7 @@ def run_ours(args):
                                    "of 1e-4, sstg_decode_tracks rebuilds the fp32 tensors bit for bit on the device)"},
             "gpu_launches": 4 * args.steps,
             "train": train,
+            "graph_construction": graph_leg,
             "clocks": sampler.result(),
             "result": {"ade": red[0].item() / red[2].item(), "fde": red[1].item() / red[2].item(),
                        "peds": int(red[2].item())},

@@ -52,6 +52,7 @@ extern "C" {
 
 /* flags of sstg_sample_ade_fde */
 #define SSTG_EVAL_FP64_DIST 1 /* per-step distance sqrt in fp64 exactly as math.sqrt in metrics.py:33,50 */
+#define SSTG_EVAL_UNIFORM_N 4 /* every scene has the same pedestrian count (= total_peds / S): skips the scene search */
 #define SSTG_EVAL_VTR_IS_REL 2 /* `Vtr` is pred_traj_rel [P,2,12] itself (utils.py:183), not the (12,N,2) V_tr blocks */
 
 #define SSTG_OK 0

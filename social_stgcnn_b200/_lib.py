@@ -17,7 +17,7 @@ N_PARAMS, N_BN, MAX_PEDS = 7563, 30, 256
 XTILE_COLS, XTILE_MAX_SCENES, XTILE_MAX_PAIRS = 128, 32, 64
 ST_PARAMS, TXP_GRAD_STRIDE, SAVE_FLOATS_PER_PED = 142, 7424, 600
 GRAPH_NORM_LAP, GRAPH_FP64, GRAPH_V_ONLY = 1, 2, 4
-EVAL_FP64_DIST, EVAL_VTR_IS_REL = 1, 2
+EVAL_FP64_DIST, EVAL_VTR_IS_REL, EVAL_UNIFORM_N = 1, 2, 4
 
 _p = C.c_void_p
 _i32, _i64, _u64 = C.c_int32, C.c_int64, C.c_uint64

@@ -26,7 +26,8 @@ namespace sstg {
 
 namespace {
 
-constexpr int E_PEDS = 64;
+constexpr int E_PEDS = 32;  // pedestrians per CTA: small CTAs (128 threads) so that 5 fit an SM and one CTA's
+                            // latency-bound prologue overlaps the sampling loops of the others
 constexpr int E_SUB = 4;
 constexpr int E_THREADS = E_PEDS * E_SUB;
 
@@ -80,12 +81,12 @@ constexpr int E_KU = 5;  // samples a thread advances together (K = 20 -> one pa
 // PHILOX : draw the noise in-kernel instead of reading eps.
 // EXTRA  : eps_out / pred_abs requested (raw_data_dict, test.py:105).
 template <bool EXACT, bool PHILOX, bool EXTRA>
-__global__ void __launch_bounds__(E_THREADS, 2)
+__global__ void __launch_bounds__(E_THREADS, 4)
 sample_ade_fde_kernel(const float* __restrict__ Vpred, const float* __restrict__ Vtr,
                       const float* __restrict__ last_obs, const int32_t* __restrict__ seg_off, int S, int K,
                       const float* __restrict__ eps, uint64_t seed, float* __restrict__ eps_out,
                       double* __restrict__ min_ade, double* __restrict__ min_fde, float* __restrict__ pred_abs,
-                      int vtr_is_rel) {
+                      int vtr_is_rel, int uniform_n) {
   using Acc = typename std::conditional<EXACT, double, float>::type;
   // [t][field][ped]: mux, muy, L00, L10, L11, gtx, gty
   __shared__ float par[T_PRED][7][E_PEDS];
@@ -100,37 +101,45 @@ sample_ade_fde_kernel(const float* __restrict__ Vpred, const float* __restrict__
   // pedestrians then need at most 6 more steps inside [s0, s0 + 64), or none at all when the
   // whole block lies in one scene (the dense-crowd case).
   __shared__ int s0_sh;
-  if (tid < 32) {
-    int lo = 0, hi = S;  // seg_off[lo] <= p_base < seg_off[hi]
-    while (hi - lo > 1) {
-      const int step = (hi - lo + 31) >> 5;
-      const int c = lo + tid * step;
-      const bool le = c < hi && seg_off[c] <= p_base;
-      const unsigned m = __ballot_sync(0xffffffffu, le);
-      const int last = 31 - __clz(m);  // lane 0 always votes (c == lo)
-      lo += last * step;
-      hi = (lo + step < hi) ? lo + step : hi;
+  if (uniform_n > 0) {  // every scene has uniform_n pedestrians (dense synthetic crowds): no search at all
+    if (tid < E_PEDS) {
+      const int p = p_base + tid;
+      sc_n0[tid] = p < P ? (p / uniform_n) * uniform_n : 0;
+      sc_N[tid] = p < P ? uniform_n : 0;
     }
-    if (tid == 0) s0_sh = lo;
-  }
-  __syncthreads();
-  if (tid < E_PEDS) {
-    const int p = p_base + tid;
-    if (p < P) {
-      int lo = s0_sh, hi = (lo + E_PEDS < S) ? lo + E_PEDS : S;
-      if (seg_off[lo + 1] > p) {
-        hi = lo + 1;
-      } else {
-        while (hi - lo > 1) {
-          const int mid = (lo + hi) >> 1;
-          if (seg_off[mid] <= p) lo = mid; else hi = mid;
-        }
+  } else {
+    if (tid < 32) {
+      int lo = 0, hi = S;  // seg_off[lo] <= p_base < seg_off[hi]
+      while (hi - lo > 1) {
+        const int step = (hi - lo + 31) >> 5;
+        const int c = lo + tid * step;
+        const bool le = c < hi && seg_off[c] <= p_base;
+        const unsigned m = __ballot_sync(0xffffffffu, le);
+        const int last = 31 - __clz(m);  // lane 0 always votes (c == lo)
+        lo += last * step;
+        hi = (lo + step < hi) ? lo + step : hi;
       }
-      sc_n0[tid] = seg_off[lo];
-      sc_N[tid] = seg_off[lo + 1] - seg_off[lo];
-    } else {
-      sc_n0[tid] = 0;
-      sc_N[tid] = 0;
+      if (tid == 0) s0_sh = lo;
+    }
+    __syncthreads();
+    if (tid < E_PEDS) {
+      const int p = p_base + tid;
+      if (p < P) {
+        int lo = s0_sh, hi = (lo + E_PEDS < S) ? lo + E_PEDS : S;
+        if (seg_off[lo + 1] > p) {
+          hi = lo + 1;
+        } else {
+          while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (seg_off[mid] <= p) lo = mid; else hi = mid;
+          }
+        }
+        sc_n0[tid] = seg_off[lo];
+        sc_N[tid] = seg_off[lo + 1] - seg_off[lo];
+      } else {
+        sc_n0[tid] = 0;
+        sc_N[tid] = 0;
+      }
     }
   }
   __syncthreads();
@@ -359,9 +368,10 @@ int launch_sample_ade_fde(const float* Vpred, const float* Vtr, const float* las
   const bool exact = flags & SSTG_EVAL_FP64_DIST, philox = eps == nullptr;
   const bool extra = eps_out != nullptr || pred_abs != nullptr;
   const int rel_in = (flags & SSTG_EVAL_VTR_IS_REL) ? 1 : 0;
+  const int uni = (flags & SSTG_EVAL_UNIFORM_N) ? P / S : 0;  // caller guarantees N_s == P / S for every scene
 #define SSTG_LAUNCH_SAMPLE(EX, PH, XT)                                                                         \
   sample_ade_fde_kernel<EX, PH, XT><<<grid, E_THREADS, 0, st>>>(Vpred, Vtr, last_obs, seg_off, S, K, eps, seed, \
-                                                                eps_out, min_ade, min_fde, pred_abs, rel_in)
+                                                                eps_out, min_ade, min_fde, pred_abs, rel_in, uni)
   if (exact) {
     if (philox) { if (extra) SSTG_LAUNCH_SAMPLE(true, true, true); else SSTG_LAUNCH_SAMPLE(true, true, false); }
     else        { if (extra) SSTG_LAUNCH_SAMPLE(true, false, true); else SSTG_LAUNCH_SAMPLE(true, false, false); }

@@ -56,6 +56,7 @@ class ScenePlan:
         self.n_tiles, self.max_n, self.a_floats, self.tile_cols = int(nt[0]), int(mx[0]), int(af[0]), int(tc[0])
         self.tile_off = self.tile_off[: self.n_tiles + 1].copy()
         self.P = int(self.seg_off[-1])
+        self.uniform = bool(S > 0 and int(n.min()) == int(n.max()))
         self._dev: Dict[torch.device, "DevicePlan"] = {}
         self._cache: Dict[tuple, list] = {}
 
@@ -227,7 +228,8 @@ def sample_ade_fde(dp: DevicePlan, Vpred, Vtr, last_obs, K: int = 20, *, eps=Non
                                              _ptr(eps), seed & (2 ** 64 - 1), _ptr(eps_out), _ptr(min_ade),
                                              _ptr(min_fde), _ptr(pred),
                                              (L.EVAL_FP64_DIST if fp64_dist else 0) |
-                                             (L.EVAL_VTR_IS_REL if vtr_is_rel else 0),
+                                             (L.EVAL_VTR_IS_REL if vtr_is_rel else 0) |
+                                             (L.EVAL_UNIFORM_N if h.uniform else 0),
                                              _stream(dev)), "sstg_sample_ade_fde")
     return {"min_ade": min_ade, "min_fde": min_fde, "eps": eps_out, "pred_abs": pred}
 
