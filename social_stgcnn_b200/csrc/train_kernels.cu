@@ -578,33 +578,34 @@ nll_fwd_bwd_kernel(const float* __restrict__ Vpred, const float* __restrict__ Vt
 // BatchNorm running statistics: r <- (1 - m) r + m s_i, scene after scene, unbiased var.
 // 30 threads; ATen's CPU kernel evaluates the update in double, so do we.
 // ---------------------------------------------------------------------------------------
-constexpr int BN_TILE = 256;  // scenes staged per pass
+constexpr int BN_TILE = 128;  // scenes staged per pass (128 x 30 doubles = 30 KB of static shared memory)
 __global__ void __launch_bounds__(256)
 bn_running_update_kernel(const float* __restrict__ stats, const int32_t* __restrict__ seg_off, int S,
                          double momentum, float* __restrict__ bn) {
   // The recurrence is sequential in the scene index, but its inputs are not: 256 threads stage a
   // tile of per-scene statistics (and element counts) in shared memory with coalesced loads, then
   // 30 threads run the recurrence over the tile out of shared memory.
-  __shared__ float st[BN_TILE * SSTG_N_BN];
-  __shared__ float cnt[BN_TILE];
+  __shared__ double st[BN_TILE * SSTG_N_BN];  // momentum * (mean | unbiased variance), ready for the recurrence
   const int i = threadIdx.x;
-  const bool is_var = (i / 5) & 1;
   double r = i < SSTG_N_BN ? static_cast<double>(bn[i]) : 0.0;
   for (int s0 = 0; s0 < S; s0 += BN_TILE) {
     const int ns = (S - s0 < BN_TILE) ? (S - s0) : BN_TILE;
-    for (int j = threadIdx.x; j < ns * SSTG_N_BN; j += blockDim.x) st[j] = stats[static_cast<size_t>(s0) * SSTG_N_BN + j];
-    for (int j = threadIdx.x; j < ns; j += blockDim.x)
-      cnt[j] = static_cast<float>(T_OBS * (seg_off[s0 + j + 1] - seg_off[s0 + j]));
+    // all threads: load, apply the unbiased-variance factor M / (M - 1) (the fp64 division is the expensive
+    // part -- done here in parallel, not inside the sequential recurrence) and the momentum
+    for (int j = threadIdx.x; j < ns * SSTG_N_BN; j += blockDim.x) {
+      const int s = j / SSTG_N_BN, k = j - s * SSTG_N_BN;
+      double v = stats[static_cast<size_t>(s0) * SSTG_N_BN + j];
+      if ((k / 5) & 1) {
+        const double M = static_cast<double>(T_OBS) * (seg_off[s0 + s + 1] - seg_off[s0 + s]);
+        v = v * M / (M - 1.0);
+      }
+      st[j] = momentum * v;
+    }
     __syncthreads();
     if (i < SSTG_N_BN) {
-      for (int s = 0; s < ns; ++s) {
-        double v = st[s * SSTG_N_BN + i];
-        if (is_var) {
-          const double M = cnt[s];
-          v = v * M / (M - 1.0);
-        }
-        r = static_cast<double>(static_cast<float>(momentum * v + (1.0 - momentum) * r));
-      }
+      const double keep = 1.0 - momentum;
+      for (int s = 0; s < ns; ++s)
+        r = static_cast<double>(static_cast<float>(st[s * SSTG_N_BN + i] + keep * r));
     }
     __syncthreads();
   }
