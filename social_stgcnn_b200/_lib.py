@@ -10,7 +10,7 @@ import os
 import threading
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libsstg.so")
+LIB_PATH = os.environ.get("SSTG_LIB") or os.path.join(_PKG, "libsstg.so")   # SSTG_LIB: A/B a differently built library
 
 T_OBS, T_PRED, C_IN, C_OUT = 8, 12, 2, 5
 N_PARAMS, N_BN, MAX_PEDS = 7563, 30, 256

@@ -49,18 +49,11 @@ __device__ __forceinline__ float warp_sum(float v) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
 }
-// sum over lanes [0, span) delivered to lane 0, when every lane >= span holds zero (narrow tiles:
-// fewer butterfly steps; span is warp-uniform and a power of two)
-__device__ __forceinline__ float warp_sum_span(float v, int span) {
-  for (int o = span >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
-}
 
 // dW[hf*6 + co][ci][kh][kw] += sum_{h, c} du[hf*6+co][h][c] * x[ci][h+kh-1][c+kw-1] over the tile's columns.
 // Packed FMAs over channel pairs: acc[pr][tap] = (dW[2pr][tap], dW[2pr+1][tap]).
 __device__ __forceinline__ void dw_unit(const float* __restrict__ DU, const float* __restrict__ XT, int Wp,
-                                        int c_end, int span, int ci, int hf, int cin, int lane,
-                                        float* __restrict__ gw) {
+                                        int c_end, int ci, int hf, int cin, int lane, float* __restrict__ gw) {
   float2 acc[3][9];
 #pragma unroll
   for (int pr = 0; pr < 3; ++pr)
@@ -97,7 +90,7 @@ __device__ __forceinline__ void dw_unit(const float* __restrict__ DU, const floa
   for (int pr = 0; pr < 3; ++pr)
 #pragma unroll
     for (int k = 0; k < 9; ++k) {
-      const float s0 = warp_sum_span(acc[pr][k].x, span), s1 = warp_sum_span(acc[pr][k].y, span);
+      const float s0 = warp_sum(acc[pr][k].x), s1 = warp_sum(acc[pr][k].y);
       if (lane == 0) {
         gw[((hf * 6 + 2 * pr) * cin + ci) * 9 + k] += s0;
         gw[((hf * 6 + 2 * pr + 1) * cin + ci) * 9 + k] += s1;
@@ -144,12 +137,6 @@ txpcnn_bwd_kernel(const float* __restrict__ dOut, const float* __restrict__ Usav
     const int cols = seg_off[s_hi] - p_lo;
     const int nsc = s_hi - s_lo;
     const int c_end = cols + nsc - 1;  // last data column of the shared tile
-    int span = 32;                     // lanes that can hold non-zero weight-gradient partials
-    while ((span >> 1) >= c_end && span > 1) span >>= 1;
-    // warps that own no column of this tile (a warp of half hf covers tile columns [32 (w%4), 32 (w%4) + 32))
-    const int busy_per_half = (cols + 31) >> 5;          // 1..4 (JX = 1) -- warps with columns, per half
-    const int n_idle = 8 - 2 * (busy_per_half < 4 ? busy_per_half : 4);
-    const int idle_rank = ((warp & 3) >= busy_per_half) ? ((warp >> 2) * (4 - busy_per_half) + (warp & 3) - busy_per_half) : -1;
     __syncthreads();
     for (int q = tid; q < cols; q += X_THREADS) {
       int j = 0;
@@ -205,17 +192,8 @@ txpcnn_bwd_kernel(const float* __restrict__ dOut, const float* __restrict__ Usav
     for (int l = 4; l >= 0; --l) {
       const int cin = (l == 0) ? 8 : 12;
       // ---- weight and bias gradients of layer l
-      // In a narrow tile only the first warp(s) of each channel half own columns and run the transposed
-      // convolution below; the others would idle at the barrier, so they take the weight-gradient units.
       float* gw = gacc + (w_base(l) - P_TP0_W);
-      if (n_idle >= 4) {
-        if (idle_rank >= 0) {
-          for (int unit = idle_rank; unit < 2 * cin; unit += n_idle)
-            dw_unit(DU, XT, Wp, c_end, span, unit >> 1, unit & 1, cin, lane, gw);
-        }
-      } else {
-        for (int unit = warp; unit < 2 * cin; unit += 8) dw_unit(DU, XT, Wp, c_end, span, unit >> 1, unit & 1, cin, lane, gw);
-      }
+      for (int unit = warp; unit < 2 * cin; unit += 8) dw_unit(DU, XT, Wp, c_end, unit >> 1, unit & 1, cin, lane, gw);
       for (int co = warp; co < 12; co += 8) {
         float sb_ = 0.f;
         for (int c = 1 + lane; c <= c_end; c += 32)
