@@ -95,9 +95,10 @@ int sstg_plan_host(const int32_t* n_peds_host, int32_t S, int32_t T, int32_t* se
 int sstg_graph_build(const float* rel, const int32_t* seg_off, const int64_t* a_off, int32_t S, int32_t T,
                      int32_t max_n, float* V, float* A, int32_t flags, void* stream) {
   const bool v_only = flags & SSTG_GRAPH_V_ONLY;
-  if (S < 0 || T <= 0 || T > 64 || max_n < 1) return SSTG_EINVAL;
+  if (S < 0 || T <= 0 || T > 64) return SSTG_EINVAL;
+  if (S == 0) return SSTG_OK;  // an empty batch is a no-op whatever the other arguments
+  if (max_n < 1) return SSTG_EINVAL;
   if (max_n > SSTG_MAX_PEDS) return SSTG_ETOOBIG;
-  if (S == 0) return SSTG_OK;
   if (!rel || !seg_off || !V || (!v_only && (!A || !a_off))) return SSTG_EINVAL;
   if (!aligned16(V) || (!v_only && !aligned16(A))) return SSTG_EINVAL;
   return launch_graph_build(rel, seg_off, a_off, S, T, max_n, V, A, flags, static_cast<cudaStream_t>(stream));
@@ -106,9 +107,10 @@ int sstg_graph_build(const float* rel, const int32_t* seg_off, const int64_t* a_
 int sstg_stgcn_forward(const float* V, const float* A, const int32_t* seg_off, const int64_t* a_off, int32_t S,
                        int32_t max_n, const float* params, const float* bn, float* H, int32_t sm_count,
                        void* stream) {
-  if (S < 0 || max_n < 1) return SSTG_EINVAL;
-  if (max_n > SSTG_MAX_PEDS) return SSTG_ETOOBIG;
+  if (S < 0) return SSTG_EINVAL;
   if (S == 0) return SSTG_OK;
+  if (max_n < 1) return SSTG_EINVAL;
+  if (max_n > SSTG_MAX_PEDS) return SSTG_ETOOBIG;
   if (!V || !A || !seg_off || !a_off || !params || !bn || !H) return SSTG_EINVAL;
   if (!aligned16(V) || !aligned16(A) || !aligned16(H)) return SSTG_EINVAL;
   return launch_stgcn_forward(V, A, seg_off, a_off, S, max_n, params, bn, H, sm_count,
@@ -117,18 +119,20 @@ int sstg_stgcn_forward(const float* V, const float* A, const int32_t* seg_off, c
 
 int sstg_stgcn_forward_fused(const float* rel, const int32_t* seg_off, int32_t S, int32_t max_n,
                              const float* params, const float* bn, float* Pws, float* H, void* stream) {
-  if (S < 0 || max_n < 1) return SSTG_EINVAL;
-  if (max_n > 64) return SSTG_ETOOBIG;
+  if (S < 0) return SSTG_EINVAL;
   if (S == 0) return SSTG_OK;
+  if (max_n < 1) return SSTG_EINVAL;
+  if (max_n > 64) return SSTG_ETOOBIG;
   if (!rel || !seg_off || !params || !bn || !Pws || !H || !aligned16(rel)) return SSTG_EINVAL;
   return launch_stgcn_forward_fused(rel, seg_off, S, max_n, params, bn, Pws, H, static_cast<cudaStream_t>(stream));
 }
 
 int sstg_txpcnn_forward(const float* H, const int32_t* seg_off, const int32_t* tile_off, int32_t n_tiles,
                         int32_t max_n, int32_t tile_cols, const float* params, float* out, void* stream) {
-  if (n_tiles < 0 || max_n < 1) return SSTG_EINVAL;
-  if (max_n > SSTG_MAX_PEDS) return SSTG_ETOOBIG;
+  if (n_tiles < 0) return SSTG_EINVAL;
   if (n_tiles == 0) return SSTG_OK;
+  if (max_n < 1) return SSTG_EINVAL;
+  if (max_n > SSTG_MAX_PEDS) return SSTG_ETOOBIG;
   if (!H || !seg_off || !tile_off || !params || !out) return SSTG_EINVAL;
   return launch_txpcnn_forward(H, seg_off, tile_off, n_tiles, max_n, params, out, nullptr, nullptr, 0, tile_cols,
                                static_cast<cudaStream_t>(stream));
@@ -190,9 +194,10 @@ int sstg_train_partial_rows(int32_t S, int32_t n_tiles, int32_t* rows_st, int32_
 int sstg_forward_train(const float* V, const float* A, const int32_t* seg_off, const int64_t* a_off,
                        const int32_t* tile_off, int32_t S, int32_t n_tiles, int32_t max_n, int32_t total_peds,
                        const float* params, float* save, float* scene_stats, float* Vpred, void* stream) {
-  if (S < 0 || n_tiles < 0 || max_n < 1 || total_peds < 0) return SSTG_EINVAL;
-  if (max_n > SSTG_MAX_PEDS) return SSTG_ETOOBIG;
+  if (S < 0 || n_tiles < 0 || total_peds < 0) return SSTG_EINVAL;
   if (S == 0) return SSTG_OK;
+  if (max_n < 1) return SSTG_EINVAL;
+  if (max_n > SSTG_MAX_PEDS) return SSTG_ETOOBIG;
   if (!V || !A || !seg_off || !a_off || !tile_off || !params || !save || !scene_stats || !Vpred) return SSTG_EINVAL;
   if (!aligned16(V)) return SSTG_EINVAL;
   const long long P = total_peds;
@@ -227,7 +232,7 @@ int sstg_backward(const float* V, const float* A, const int32_t* seg_off, const 
                   const int32_t* tile_off, int32_t S, int32_t n_tiles, int32_t max_n, int32_t total_peds,
                   const float* params, const float* save, const float* scene_stats, const float* dVpred,
                   float* dH_ws, float* partial_st, float* partial_tx, float* grad, void* stream) {
-  if (S < 0 || n_tiles < 0 || max_n < 1 || total_peds < 0) return SSTG_EINVAL;
+  if (S < 0 || n_tiles < 0 || total_peds < 0 || (S > 0 && max_n < 1)) return SSTG_EINVAL;
   if (max_n > SSTG_MAX_PEDS) return SSTG_ETOOBIG;
   if (!grad) return SSTG_EINVAL;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -293,7 +298,7 @@ int sstg_train_step(const float* obs_rel, const float* pred_rel, const int32_t* 
                     int64_t a_floats, float* params, float* bn, const float* scene_weight, float* ws,
                     int64_t ws_floats, float lr, float clip_norm, double bn_momentum, int32_t graph_flags,
                     float* loss, float* grad, float* group_loss, void* stream) {
-  if (S < 0 || n_tiles < 0 || max_n < 1 || total_peds < 0 || a_floats < 0) return SSTG_EINVAL;
+  if (S < 0 || n_tiles < 0 || total_peds < 0 || a_floats < 0 || (S > 0 && max_n < 1)) return SSTG_EINVAL;
   if (max_n > SSTG_MAX_PEDS) return SSTG_ETOOBIG;
   if (!params || !bn || !grad || !loss) return SSTG_EINVAL;
   if (S == 0) return sstg_backward(nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0, 1, 0, nullptr, nullptr, nullptr,

@@ -300,3 +300,62 @@ def test_fused_graph_stgcn_front(golden, batch, dev, ckpt):
     big = sstg.ScenePlan([65, 3])
     with pytest.raises(ValueError):
         sstg.stgcn_forward_fused(big.on(dev), torch.zeros(68, 2, 8, device=dev), p, b)
+
+
+def test_edge_cases_single_pedestrian_odd_T_and_empty(golden, dev):
+    """Edges the packed layout must survive: scenes of ONE pedestrian (A = [[0]]: d = 1), scenes of two,
+    mixed with a 64-pedestrian scene; a graph with T = 5 (general kernel, T % 4 != 0); an empty batch."""
+    import social_stgcnn_b200 as sstg
+    from oracle import stgcnn_oracle as O
+    n_list = [1, 2, 1, 64, 1, 3]
+    obs_rel, pred_rel, obs_abs = O.synthetic_scenes(1, sum(n_list), seed=31)
+    last = np.ascontiguousarray(obs_abs[:, :, -1])
+    plan = sstg.ScenePlan(n_list)
+    params, bn = golden.params("eth")
+    eng = sstg.InferenceEngine(params, bn, dev)
+    t = lambda a: torch.from_numpy(a).to(dev)
+    P_, S_ = O.unflatten_params(params), O.unflatten_bn(bn)
+    for fused in (False, True):
+        r = eng.infer(plan, t(obs_rel), t(pred_rel), t(last), K=20, seed=2, fused=fused, fp64_dist=True, want_eps=True,
+                      graph_fp64=not fused)
+        torch.cuda.synchronize()
+        vp, eps = r["V_pred"].cpu().numpy(), r["eps"].cpu().numpy()
+        ade = r["min_ade"].cpu().numpy()
+        for i, n in enumerate(n_list):
+            o = int(plan.seg_off[i])
+            V_ref, A_ref = O.seq_to_graph(obs_rel[o:o + n])
+            if not fused:
+                a = r["A_obs"].cpu().numpy()[plan.a_off[i]:plan.a_off[i] + 8 * n * n].reshape(8, n, n)
+                assert np.array_equal(a.view(np.uint32), A_ref.view(np.uint32)), n
+                if n == 1:
+                    assert np.all(a == 0)
+            with torch.no_grad():
+                out = O.model_forward(P_, S_, V_ref, A_ref).numpy()
+            got = vp[o * 60:(o + n) * 60].reshape(1, 5, 12, n)
+            assert rel_err(got, out) < TOL, (n, fused)
+            vt = np.ascontiguousarray(pred_rel[o:o + n].transpose(2, 0, 1))
+            oa, _, _ = O.sample_ade_fde(got[0].transpose(1, 2, 0), vt, last[o:o + n],
+                                        eps[o * 480:(o + n) * 480].reshape(20, 12, n, 2))
+            assert np.abs(ade[o:o + n] - oa).max() < 2e-6 * max(1.0, oa.max())
+    # T = 5 graph (neither 8 nor 12): the general kernel, bit-exact in fp64 mode, close in fp32 mode
+    rel5 = np.ascontiguousarray(obs_rel[:, :, :5])
+    p5 = sstg.ScenePlan(n_list, T=5)
+    for fp64 in (True, False):
+        V, A = sstg.graph_build(p5.on(dev), t(rel5), 5, fp64=fp64)
+        torch.cuda.synchronize()
+        A = A.cpu().numpy()
+        for i, n in enumerate(n_list):
+            o = int(p5.seg_off[i])
+            _, A_ref = O.seq_to_graph(rel5[o:o + n])
+            a = A[p5.a_off[i]:p5.a_off[i] + 5 * n * n].reshape(5, n, n)
+            if fp64:
+                assert np.array_equal(a.view(np.uint32), A_ref.view(np.uint32)), n
+            else:
+                assert np.abs(a - A_ref).max() < 2e-6
+    # empty batch: every entry point is a no-op
+    e = sstg.ScenePlan([])
+    z = torch.zeros(0, 2, 8, device=dev)
+    V, A = sstg.graph_build(e.on(dev), z, 8)
+    H = sstg.stgcn_forward(e.on(dev), V, torch.zeros(4, device=dev), t(params), t(bn))
+    out = sstg.txpcnn_forward(e.on(dev), H, t(params))
+    assert V.numel() == 0 and out.numel() == 0
