@@ -86,16 +86,39 @@ __device__ __forceinline__ void dw_unit(const float* __restrict__ DU, const floa
           }
     }
   }
+  // ---- warp reduction of the 54 partial sums (padded to 64) as a reduce-scatter: at every butterfly
+  // step a lane hands over the half of its values its partner keeps, so 32+16+8+4+2 = 62 shuffles
+  // (instead of 54 x 5) leave lane L with the totals of values 2L and 2L+1, and the lanes then update
+  // the accumulator in parallel.
+  float v[64];
+#pragma unroll
+  for (int i = 0; i < 64; ++i) v[i] = 0.f;
 #pragma unroll
   for (int pr = 0; pr < 3; ++pr)
 #pragma unroll
     for (int k = 0; k < 9; ++k) {
-      const float s0 = warp_sum(acc[pr][k].x), s1 = warp_sum(acc[pr][k].y);
-      if (lane == 0) {
-        gw[((hf * 6 + 2 * pr) * cin + ci) * 9 + k] += s0;
-        gw[((hf * 6 + 2 * pr + 1) * cin + ci) * 9 + k] += s1;
-      }
+      v[(pr * 9 + k) * 2] = acc[pr][k].x;
+      v[(pr * 9 + k) * 2 + 1] = acc[pr][k].y;
     }
+#pragma unroll
+  for (int half = 32; half >= 2; half >>= 1) {
+    const int o = half >> 1;                       // 16, 8, 4, 2, 1
+    const bool up = (lane & o) != 0;               // this lane keeps the upper half
+#pragma unroll
+    for (int i = 0; i < half; ++i) {
+      const float send = up ? v[i] : v[i + half];
+      const float keep = up ? v[i + half] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    const int idx = 2 * lane + j;                  // value index: (pr*9 + k)*2 + e, 54 of them
+    if (idx < 54) {
+      const int e = idx & 1, pk = idx >> 1, pr = pk / 9, k = pk - pr * 9;
+      gw[((hf * 6 + 2 * pr + e) * cin + ci) * 9 + k] += v[j];
+    }
+  }
 }
 
 template <int JX>
