@@ -23,46 +23,6 @@ struct XSmem {
   int nstr[2 * X_COLS];  // tile column -> N of its scene (row stride in global memory)
 };
 
-// one 3x3 layer for one column: acc[6][5] += W[half] * patch
-template <int CI>
-__device__ __forceinline__ void conv_column(const float* __restrict__ act, int Wp, int sc,
-                                            const float* __restrict__ wl, int half, float (&acc)[6][5]) {
-#pragma unroll 2
-  for (int ci = 0; ci < CI; ++ci) {
-    float x[5][3];
-    const float* a = act + (ci * 5) * Wp + sc - 1;
-#pragma unroll
-    for (int h = 0; h < 5; ++h) {
-      x[h][0] = a[h * Wp + 0];
-      x[h][1] = a[h * Wp + 1];
-      x[h][2] = a[h * Wp + 2];
-    }
-    const float4* w4 = reinterpret_cast<const float4*>(wl + (ci * 2 + half) * X_WSLOT);
-    float w[X_WSLOT];
-#pragma unroll
-    for (int i = 0; i < X_WSLOT / 4; ++i) {
-      const float4 v = w4[i];
-      w[4 * i + 0] = v.x;
-      w[4 * i + 1] = v.y;
-      w[4 * i + 2] = v.z;
-      w[4 * i + 3] = v.w;
-    }
-#pragma unroll
-    for (int co = 0; co < 6; ++co)
-#pragma unroll
-      for (int kh = 0; kh < 3; ++kh)
-#pragma unroll
-        for (int kw = 0; kw < 3; ++kw) {
-          const float wv = w[co * 9 + kh * 3 + kw];
-#pragma unroll
-          for (int h = 0; h < 5; ++h) {
-            const int hi = h + kh - 1;
-            if (hi >= 0 && hi < 5) acc[co][h] = fmaf(wv, x[hi][kw], acc[co][h]);
-          }
-        }
-  }
-}
-
 // ---- packed FP32 (sm_100 FFMA2): d.xy = a.xy * b.xy + d.xy, two IEEE fp32 FMAs in one issue slot
 __device__ __forceinline__ void ffma2(float2& d, const float2 a, const float2 b) {
   asm("fma.rn.f32x2 %0, %1, %2, %0;"

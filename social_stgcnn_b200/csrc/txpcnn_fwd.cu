@@ -10,19 +10,24 @@
 // as 40 rows of N, and the 60 output rows of N ARE the (5,12,N) result: no data movement.
 //
 // This kernel is FP32-FMA bound (56,160 FMA per pedestrian column against 400 bytes), so
-// the design goal is FFMA issue density:
+// the design goal is FMA-pipe utilisation:
 //   * a CTA owns a TILE of whole scenes, up to 128 pedestrian columns (one scene of up to
 //     256 if it is larger); tiny real-data scenes share a tile.  In shared memory every
 //     scene is separated by one permanently-zero column, which implements the conv's zero
 //     padding in the pedestrian axis and stops neighbouring scenes bleeding into each
 //     other without a single select in the inner loop.
 //   * 256 threads = 2 output-channel halves x 128 columns.  A thread keeps the 6x5
-//     accumulators of its column in registers; per input channel it loads the 5x3 input
-//     patch (conflict-free LDS) and streams 54 weights as warp-uniform LDS.128 broadcasts:
-//     234 FFMA per 29 shared loads.
-//   * the five layers run in place in ONE 60-row activation tile (two barriers per layer),
-//     which keeps the CTA at ~56 KB of shared memory and 4 CTAs (32 warps) per SM.
+//     accumulators of its column as 3x5 packed float2 (channel pairs) and issues
+//     fma.rn.f32x2 (SASS FFMA2: two fp32 FMAs per issue slot); per input channel it loads the
+//     5x3 input patch (conflict-free LDS, duplicated into pairs) and streams 54 tap-major
+//     weights as warp-uniform LDS.128 broadcasts: 117 FFMA2 per 29 shared loads.
+//   * the tile's 40 input rows arrive by 20 cp.async per thread (one wait), and the five layers
+//     run in place in ONE 60-row activation tile (two barriers per layer): ~68 KB of shared
+//     memory and 128 registers -> 2 CTAs (16 warps) per SM.
 //   * persistent grid: weights are re-laid out into shared memory once per CTA.
+// Inference on scenes of up to 128 pedestrians uses the Winograd kernel of txpcnn_wino.cu instead;
+// this direct kernel serves training (SAVE: it also stores every layer's pre-activation and
+// output for the backward pass) and larger scenes.
 #include "txpcnn_common.cuh"
 
 namespace sstg {
