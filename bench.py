@@ -288,7 +288,28 @@ def run_train_leg(dev, world, rank, steps, warmup, batch=128):
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms = float(ms[0])
     peds = float(np.mean([g[0].sum() for g in groups]))
+    indep = None
+    if world > 1:
+        # the reference's own multi-GPU recipe (train.sh:4-18): independent trainings side by side, one per GPU,
+        # no collective at all -- every rank trains its own replica on its own groups
+        eng2 = sstg.TrainEngine(params, bn, dev)
+        for i in range(warmup):
+            eng2.step(groups[i % len(groups)][1], groups[i % len(groups)][2], groups[i % len(groups)][3], batch, 1e-4)
+        dist.barrier()
+        torch.cuda.synchronize()
+        i0, i1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        i0.record()
+        for i in range(steps):
+            g = groups[i % len(groups)]
+            eng2.step(g[1], g[2], g[3], batch, 1e-4)
+        i1.record()
+        torch.cuda.synchronize()
+        t2 = torch.tensor([i0.elapsed_time(i1)], dtype=torch.float64, device=dev)
+        dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+        indep = {"value": world * batch * steps / (float(t2[0]) * 1e-3), "unit": "scenes/s",
+                 "what": "independent trainings, one per GPU, as the reference's train.sh launches them (no collective)"}
     return {"value": batch * steps / (ms * 1e-3), "unit": "scenes/s", "ms_per_group": ms / steps, "batch": batch,
+            "independent_replicas": indep,
             "groups_timed": steps, "mean_peds_per_group": peds, "n_gpus": world,
             "what": "train(): graph build + train-mode fwd (per-scene BN stats) + NLL + full bwd + BN running stats "
                     "+ SGD, one packed ragged group of 128 ETH/UCY-shaped scenes per step"
