@@ -64,6 +64,11 @@ def synth_batch(num_scenes, n_peds, seed, compact=False):
     return out
 
 
+def workload_name(scenes_per_gpu):
+    return (f"synthetic dense crowds: {scenes_per_gpu} scenes/GPU x {N_PEDS} peds (config 3: 1M scenes at 8 GPUs with "
+            f"the default shard), obs 8 -> pred 12, K={K_SAMPLES} Philox samples, eth checkpoint weights")
+
+
 def load_weights():
     w = np.load(os.path.join(ROOT, "tests", "golden", "weights.npz"))
     return w["eth.params"], w["eth.bn"]
@@ -189,8 +194,9 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / max(1, args.steps), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"synthetic dense crowds, {N_PEDS} peds/scene, obs 8 -> pred 12, K={K_SAMPLES}; "
-                               f"bounded sample of {per_step} scenes per step"},
+        "config": {"workload": workload_name(args.scenes_per_gpu), "scenes_per_gpu": args.scenes_per_gpu,
+                   "peds_per_scene": N_PEDS, "ksteps": K_SAMPLES,
+                   "sample_per_step": f"{per_step} scenes of this workload per step (bounded CPU sample)"},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": f"{done} scenes in {dt:.1f}s, oracle port (vectorised numpy graph build + torch "
                                    f"CPU fp32 forward + numpy sampling), one process per core"},
@@ -477,9 +483,7 @@ def run_ours(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"synthetic dense crowds: {S} scenes/GPU x {N} peds (config 3: 1M scenes at 8 GPUs "
-                                   f"with the default shard), obs 8 -> pred 12, K={K_SAMPLES} Philox samples, "
-                                   f"eth checkpoint weights",
+            "config": {"workload": workload_name(S),
                        "scenes_per_gpu": S, "peds_per_scene": N, "ksteps": K_SAMPLES, "graph_mode": "fp32",
                        "l2_policy": "inputs larger than L2 (A is %.1f GB per step)" % (plan.a_floats * 4 / 1e9),
                        "parallelism": f"scene-sharded x{world}, no data-path collective",
