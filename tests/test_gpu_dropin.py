@@ -286,3 +286,25 @@ def test_compact_host_format_is_bit_exact(golden, dev):
     a2, f2 = eng.infer_host(d.plan_obs, None, None, None, 20, chunk_scenes=16, seed=1,
                             compact=(start.pin_memory(), delta.pin_memory()))
     assert np.array_equal(a1, a2) and np.array_equal(f1, f2)
+
+
+def test_validate_epoch_and_sharded_evaluator(golden, dev):
+    """driver.validate_epoch == vald() of train.py:81-122 replayed on the reference's own per-scene eval
+    NLLs (golden), and parallel.ShardedEvaluator at world size 1 == driver.evaluate."""
+    import social_stgcnn_b200 as sstg
+    from social_stgcnn_b200 import driver, parallel
+    from social_stgcnn_b200.utils import TrajectoryDataset
+    d = TrajectoryDataset(os.path.join(GOLD, "datasets", "eth", "test") + "/", obs_len=8, pred_len=12, skip=1,
+                          norm_lap_matr=True, device=dev)
+    params, bn = golden.params("eth")
+    eng = sstg.InferenceEngine(params, bn, dev)
+    nll = golden.loss["eth.nll_eval"][:70]
+    for bs in (16, 128, 7):
+        ref = sum(float(nll[g0:g0 + bs][:-1].sum()) / bs for g0 in range(0, 70, bs)) / 70
+        got = driver.validate_epoch(d, eng, bs)
+        assert abs(got - ref) < 1e-5 * max(1.0, abs(ref)), (bs, got, ref)
+    a1, f1, _ = driver.evaluate(d, eng, KSTEPS=20, seed=5, exact=False)
+    ev = parallel.ShardedEvaluator(eng)
+    a2, f2, n = ev.evaluate(d.plan_obs.n_peds, d.obs_traj_rel, d.pred_traj_rel, d.obs_traj[:, :, -1].contiguous(),
+                            K=20, seed=5)
+    assert n == 181 and abs(a1 - a2) < 1e-12 and abs(f1 - f2) < 1e-12
