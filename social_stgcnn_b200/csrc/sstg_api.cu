@@ -78,7 +78,7 @@ int sstg_plan_host(const int32_t* n_peds_host, int32_t S, int32_t T, int32_t* se
     if (wcol + 1 > wmax) wmax = wcol + 1;
     ++scenes;
     ped += n;
-    if (ped > INT32_MAX / 64) return SSTG_ETOOBIG;  // int32 element offsets inside the kernels
+    if (ped > INT32_MAX / 2) return SSTG_ETOOBIG;  // pedestrian indices are int32 (element offsets are 64-bit)
     seg_off_host[s + 1] = static_cast<int32_t>(ped);
     af += static_cast<int64_t>(T) * n * n;
     af = (af + 3) & ~int64_t(3);  // every scene block starts 16-byte aligned
