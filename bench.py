@@ -318,7 +318,8 @@ def run_train_leg(dev, world, rank, steps, warmup, batch=128):
             "independent_replicas": indep,
             "groups_timed": steps, "mean_peds_per_group": peds, "n_gpus": world,
             "what": "train(): graph build + train-mode fwd (per-scene BN stats) + NLL + full bwd + BN running stats "
-                    "+ SGD, one packed ragged group of 128 ETH/UCY-shaped scenes per step"
+                    "+ SGD, one packed ragged group of 128 ETH/UCY-shaped scenes per step (8 distinct groups cycled; a "
+                    "group's working set, ~3 MB, is L2-resident by nature -- the step is latency-bound, not bandwidth-bound)"
                     + ("; group sharded over ranks, NCCL all-reduce of the 7,563-float gradient" if world > 1 else "")}
 
 

@@ -207,27 +207,39 @@ graph_build_fast_kernel(const float* __restrict__ rel, const int32_t* __restrict
   const int groups = T / F_WARPS;
   const long long items = static_cast<long long>(S) * groups;
 
-  // software pipeline: the (<= 128) float4 of the NEXT item's displacements and its offsets are
-  // fetched into registers while the current item is computed
+  // Two-level software pipeline: the offsets (seg_off, a_off) of the item AFTER the next one and the
+  // displacement float4 of the NEXT item are in flight while the current item is computed, so neither the
+  // dependent offset -> address -> data chain nor the data load is ever waited for.
   long long it = blockIdx.x;
-  int s = 0, t0 = 0, n0 = 0, N = 0;
+  int t0 = 0, n0 = 0, N = 0;             // item whose `pre` is in registers (current at the loop top)
   long long ao = 0;
+  int q_n0 = 0, q_N = 0;                 // offsets of the item after it
+  long long q_ao = 0;
   float4 pre = make_float4(0.f, 0.f, 0.f, 0.f);
-  auto fetch = [&](long long item) {
-    s = static_cast<int>(item / groups);
-    t0 = static_cast<int>(item - static_cast<long long>(s) * groups) * F_WARPS;
-    n0 = seg_off[s];
-    N = seg_off[s + 1] - n0;
-    ao = a_off[s];
+  auto load_offsets = [&](long long item) {
+    const int sc = static_cast<int>(item / groups);
+    q_n0 = seg_off[sc];
+    q_N = seg_off[sc + 1] - q_n0;
+    q_ao = a_off[sc];
+  };
+  auto load_rel = [&](long long item) {  // uses the offsets already in q_*
+    const int sc = static_cast<int>(item / groups);
+    t0 = static_cast<int>(item - static_cast<long long>(sc) * groups) * F_WARPS;
+    n0 = q_n0;
+    N = q_N;
+    ao = q_ao;
     if (tid < 2 * N)  // tid = p*2 + c: one 16-byte run of 4 timesteps
       pre = *reinterpret_cast<const float4*>(rel + (static_cast<size_t>(n0) * 2 + tid) * T + t0);
   };
-  if (it < items) fetch(it);
+  if (it < items) {
+    load_offsets(it);
+    load_rel(it);
+    if (it + gridDim.x < items) load_offsets(it + gridDim.x);
+  }
 
   while (it < items) {
-    const int cs = s, ct0 = t0, cn0 = n0, cN = N;
+    const int ct0 = t0, cn0 = n0, cN = N;
     const long long cao = ao;
-    (void)cs;
     if (tid < 2 * cN) {
       float* dst = ((tid & 1) ? ys : xs) + (tid >> 1);
       dst[0] = pre.x;
@@ -237,7 +249,10 @@ graph_build_fast_kernel(const float* __restrict__ rel, const int32_t* __restrict
     }
     __syncthreads();
     it += gridDim.x;
-    if (it < items) fetch(it);
+    if (it < items) {
+      load_rel(it);                                                 // offsets arrived an iteration ago
+      if (it + gridDim.x < items) load_offsets(it + gridDim.x);     // consumed an iteration from now
+    }
 
     float2* Vs = reinterpret_cast<float2*>(V + static_cast<size_t>(cn0) * T * 2) + static_cast<size_t>(ct0) * cN;
     for (int i = tid; i < cN * F_WARPS; i += F_THREADS) {
@@ -261,9 +276,11 @@ graph_build_fast_kernel(const float* __restrict__ rel, const int32_t* __restrict
       // ---- pass 1: weights once, column sums on the fly (4 rows per iteration)
       float* wp = Wt + lane;
       int h = 0;
+      float4 xn = *reinterpret_cast<const float4*>(xt), yn = *reinterpret_cast<const float4*>(yt);
       for (; h + 4 <= cN; h += 4) {
-        const float4 xh = *reinterpret_cast<const float4*>(xt + h);
-        const float4 yh = *reinterpret_cast<const float4*>(yt + h);
+        const float4 xh = xn, yh = yn;  // loaded one group ahead (the read past row N stays inside the padded row)
+        xn = *reinterpret_cast<const float4*>(xt + ((h + 4 < NP) ? h + 4 : h));
+        yn = *reinterpret_cast<const float4*>(yt + ((h + 4 < NP) ? h + 4 : h));
         const float xa[4] = {xh.x, xh.y, xh.z, xh.w}, ya[4] = {yh.x, yh.y, yh.z, yh.w};
 #pragma unroll
         for (int u = 0; u < 4; ++u) {

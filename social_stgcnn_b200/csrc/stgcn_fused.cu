@@ -64,17 +64,27 @@ graph_agg_kernel(const float* __restrict__ rel, const int32_t* __restrict__ seg_
     if (c == 0) fp.a1 = params[P_PRELU1];
   }
 
+  // two-level software pipeline (see graph_build_fast_kernel): offsets two items ahead, data one item ahead
   long long it = blockIdx.x;
-  int s = 0, t0 = 0, n0 = 0, N = 0;
+  int t0 = 0, n0 = 0, N = 0, q_n0 = 0, q_N = 0;
   float4 pre = make_float4(0.f, 0.f, 0.f, 0.f);
-  auto fetch = [&](long long item) {
-    s = static_cast<int>(item / groups);
-    t0 = static_cast<int>(item - static_cast<long long>(s) * groups) * U_WARPS;
-    n0 = seg_off[s];
-    N = seg_off[s + 1] - n0;
+  auto load_offsets = [&](long long item) {
+    const int sc = static_cast<int>(item / groups);
+    q_n0 = seg_off[sc];
+    q_N = seg_off[sc + 1] - q_n0;
+  };
+  auto load_rel = [&](long long item) {
+    const int sc = static_cast<int>(item / groups);
+    t0 = static_cast<int>(item - static_cast<long long>(sc) * groups) * U_WARPS;
+    n0 = q_n0;
+    N = q_N;
     if (tid < 2 * N) pre = *reinterpret_cast<const float4*>(rel + (static_cast<size_t>(n0) * 2 + tid) * T + t0);
   };
-  if (it < items) fetch(it);
+  if (it < items) {
+    load_offsets(it);
+    load_rel(it);
+    if (it + gridDim.x < items) load_offsets(it + gridDim.x);
+  }
 
   while (it < items) {
     const int ct0 = t0, cn0 = n0, cN = N;
@@ -87,7 +97,10 @@ graph_agg_kernel(const float* __restrict__ rel, const int32_t* __restrict__ seg_
     }
     __syncthreads();  // also publishes fp on the first trip
     it += gridDim.x;
-    if (it < items) fetch(it);
+    if (it < items) {
+      load_rel(it);
+      if (it + gridDim.x < items) load_offsets(it + gridDim.x);
+    }
 
     const float* xt = xs + warp * NP;
     const float* yt = ys + warp * NP;
@@ -104,9 +117,11 @@ graph_agg_kernel(const float* __restrict__ rel, const int32_t* __restrict__ seg_
     // ---- pass 1: inverse distances once, column sums on the fly
     float* wp = Wt + lane;
     int h = 0;
+    float4 xn = *reinterpret_cast<const float4*>(xt), yn = *reinterpret_cast<const float4*>(yt);
     for (; h + 4 <= cN; h += 4) {
-      const float4 xh = *reinterpret_cast<const float4*>(xt + h);
-      const float4 yh = *reinterpret_cast<const float4*>(yt + h);
+      const float4 xh = xn, yh = yn;  // loaded one group ahead (the read past row N stays inside the padded row)
+      xn = *reinterpret_cast<const float4*>(xt + ((h + 4 < NP) ? h + 4 : h));
+      yn = *reinterpret_cast<const float4*>(yt + ((h + 4 < NP) ? h + 4 : h));
       const float xa[4] = {xh.x, xh.y, xh.z, xh.w}, ya[4] = {yh.x, yh.y, yh.z, yh.w};
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
