@@ -244,6 +244,36 @@ def run_graph_leg(dev, steps=5, num_scenes=262144):
 
 
 # ---------------------------------------------------------------------------------
+# ragged inference leg (BASELINE.json config 1 shapes): real-data-sized scenes, packed
+# ---------------------------------------------------------------------------------
+def run_ragged_leg(dev, steps=5, num_scenes=65536):
+    """scenes/s of graph build + forward + 20-sample ADE/FDE on a packed batch of ETH/UCY-shaped scenes
+    (2..57 pedestrians, median ~6): the shape of the reference's own test.py workload, where it runs one
+    scene per iteration."""
+    import torch
+    import social_stgcnn_b200 as sstg
+    params, bn = load_weights()
+    eng = sstg.InferenceEngine(params, bn, dev)
+    n = synth_ragged_counts(num_scenes, 17)
+    obs, pred, last = synth_batch(int(n.sum()), 1, 4242)
+    obs, pred, last = obs.to(dev), pred.to(dev), last.to(dev)
+    plan = sstg.ScenePlan(n)
+    out = {"scenes": num_scenes, "pedestrians": int(n.sum()), "peds_per_scene": "2..57, log-normal, median 6"}
+    for name, fused in (("scenes_per_s", False), ("fused_scenes_per_s", True)):
+        for _ in range(3):
+            eng.infer(plan, obs, pred, last, K_SAMPLES, seed=1, want_vtr=False, fused=fused)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            eng.infer(plan, obs, pred, last, K_SAMPLES, seed=1, want_vtr=False, fused=fused)
+        e1.record()
+        torch.cuda.synchronize()
+        out[name] = num_scenes * steps / (e0.elapsed_time(e1) * 1e-3)
+    return out
+
+
+# ---------------------------------------------------------------------------------
 # training leg (BASELINE.json config 2): optimiser groups of 128 ragged scenes
 # ---------------------------------------------------------------------------------
 def synth_ragged_counts(num_scenes, seed):
@@ -454,11 +484,12 @@ def run_ours(args):
     c1.record()
     torch.cuda.synchronize()
     h2d_gbs = (obs_h.numel() + pred_h.numel()) * 4 / (c0.elapsed_time(c1) * 1e-3) / 1e9
-    train = graph_leg = None
+    train = graph_leg = ragged_leg = None
     if not args.no_train:
         train = run_train_leg(dev, world, rank, steps=max(20, 10 * args.steps), warmup=5)
         if rank == 0:
             graph_leg = run_graph_leg(dev)
+            ragged_leg = run_ragged_leg(dev)
 
     t = torch.tensor([ms_total, ms_e2e, ms_e2e_c, ms_fused], dtype=torch.float64, device=dev)
     red = torch.tensor([sum_a, sum_f, float(plan.P)], dtype=torch.float64, device=dev)
@@ -515,6 +546,7 @@ def run_ours(args):
             "gpu_launches": 4 * args.steps,
             "train": train,
             "graph_construction": graph_leg,
+            "ragged_inference": ragged_leg,
             "clocks": sampler.result(),
             "result": {"ade": red[0].item() / red[2].item(), "fde": red[1].item() / red[2].item(),
                        "peds": int(red[2].item())},

@@ -105,7 +105,7 @@ def test_graph_no_laplacian(golden, batch, dev):
         assert np.array_equal(_scene_A(A, plan, i), w), name
 
 
-@pytest.mark.parametrize("ckpt", ["eth", "zara1"])
+@pytest.mark.parametrize("ckpt", ["eth", "hotel", "univ", "zara1", "zara2"])
 def test_forward_eval_vs_reference(golden, batch, dev, ckpt):
     """st_gcn + TXP-CNN on the reference's own A (fp64-mode graph == reference bitwise):
     V_pred within 1e-5 of the reference's eval forward for every golden scene."""
@@ -275,7 +275,7 @@ def test_infer_host_pipelined_chunks_equal_direct_calls(golden, batch, dev):
     assert len(plan.chunks(7)) == (plan.S + 6) // 7
 
 
-@pytest.mark.parametrize("ckpt", ["eth", "zara1"])
+@pytest.mark.parametrize("ckpt", ["eth", "hotel", "univ", "zara1", "zara2"])
 def test_fused_graph_stgcn_front(golden, batch, dev, ckpt):
     """sstg_stgcn_forward_fused (graph + st_gcn with the adjacency kept in shared memory) against
     the unfused pair on the same inputs and, through the TXP-CNN, against the reference's V_pred."""

@@ -46,7 +46,7 @@ def test_graph_zero_distance_and_no_laplacian(golden):
 
 
 def test_forward_eval_and_train(golden):
-    for ckpt in ("eth", "zara1"):
+    for ckpt in ("eth", "hotel", "univ", "zara1", "zara2"):    # the five shipped checkpoints
         params, bn = golden.params(ckpt)
         P, S = O.unflatten_params(params), O.unflatten_bn(bn)
         for name in golden.names:
