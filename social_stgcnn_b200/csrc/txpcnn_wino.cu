@@ -27,6 +27,9 @@ namespace {
 
 using namespace txp;
 
+#ifndef WINO_NPF
+#define WINO_NPF 3  // filter vectors in flight ahead of their use (tuning knob; 2..4 measured)
+#endif
 constexpr int W_PAIRS = SSTG_XTILE_MAX_PAIRS;  // 64 column pairs per tile
 constexpr int W_U0 = 8 * 3 * 12 * 4;           // layer 0: [ci 8][kh 3][co 12][4]
 constexpr int W_UL = 12 * 3 * 12 * 4;          // layers 1..4
@@ -161,7 +164,7 @@ txpcnn_wino_kernel(const float* __restrict__ Hin, const int32_t* __restrict__ se
         // while the 10 FFMA2 of the current (kh, channel) step issue.
         const float* Ul = sm.U + (l == 0 ? 0 : W_U0 + (l - 1) * W_UL) + co0 * 4;
         const int CI = (l == 0) ? 8 : 12;
-        constexpr int STEPS = 3 * COT, NPF = 3;
+        constexpr int STEPS = 3 * COT, NPF = WINO_NPF;
         const float* a = act + sc0 - 1;  // even offset: aligned float2 loads
         float2 d01[5], d23[5];
 #pragma unroll
