@@ -484,6 +484,19 @@ def run_ours(args):
     c1.record()
     torch.cuda.synchronize()
     h2d_gbs = (obs_h.numel() + pred_h.numel()) * 4 / (c0.elapsed_time(c1) * 1e-3) / 1e9
+    # ---- live device copy bandwidth (the same recipe as MEASURED_PEAKS.json: b.copy_(a), read + write bytes)
+    ca = torch.empty(256 * 1024 * 1024, dtype=torch.float32, device=dev)
+    cb = torch.empty_like(ca)
+    best = 1e9
+    for _ in range(6):
+        q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        q0.record()
+        cb.copy_(ca)
+        q1.record()
+        torch.cuda.synchronize()
+        best = min(best, q0.elapsed_time(q1))
+    copy_gbs = 2 * ca.numel() * 4 / (best * 1e-3) / 1e9
+    del ca, cb
     train = graph_leg = ragged_leg = None
     if not args.no_train:
         train = run_train_leg(dev, world, rank, steps=max(20, 10 * args.steps), warmup=5)
@@ -526,6 +539,7 @@ def run_ours(args):
                          "traffic_source": (f"ncu --set full, {tr['file']}: {tr['dram_bytes']} B for a launch of "
                                             f"{tr['scenes']} scenes, scaled to this launch" if tr else None),
                          "algorithmic_bytes_per_launch": bytes_s, "peak_source": peak_src,
+                         "copy_GBps_live": round(copy_gbs, 1),
                          "share_of_step": kern_ms["stgcn_forward"] / ksum},
             "kernels": kernels,
             "e2e": {"value": S * world * args.steps / (ms_e2e * 1e-3), "unit": UNIT,
