@@ -21,7 +21,6 @@ import numpy as np
 import torch
 from torch.utils.data import Dataset
 
-from . import _lib as L
 from .engine import ScenePlan, graph_build
 
 
