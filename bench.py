@@ -287,42 +287,57 @@ def synth_ragged_counts(num_scenes, seed):
 def run_train_leg(dev, world, rank, steps, warmup, batch=128):
     """scenes/s of train() (graph build + train-mode forward + NLL + backward + BN stats + SGD)
     on packed groups of `batch` scenes; with world > 1 every group is sharded over the ranks and
-    the 7,563-float gradient is all-reduced over NCCL.  Device timing, max over ranks."""
+    gradient / loss / BN statistics are exchanged over NVLink peer memory by libsstg's fused
+    exchange+SGD kernel (the NCCL all-reduce variant is timed beside it).  Device timing, max over ranks."""
     import torch
     import torch.distributed as dist
     import social_stgcnn_b200 as sstg
     from social_stgcnn_b200 import parallel as Pl
     params, bn = load_weights()
-    eng = sstg.TrainEngine(params, bn, dev)
-    trainer = Pl.DistributedTrainer(eng) if world > 1 else None
     groups = []
     for g in range(8):                                    # 8 distinct groups, cycled
         n = synth_ragged_counts(batch, 100 + g)
         obs, pred, _ = synth_batch(int(n.sum()), 1, 7000 + g)
         groups.append((n, sstg.ScenePlan(n), obs.to(dev), pred.to(dev)))
 
-    def one(i):
-        n, plan, obs, pred = groups[i % len(groups)]
-        if trainer is not None:
-            trainer.step(n, obs, pred, batch, 1e-4)
-        else:
-            eng.step(plan, obs, pred, batch, 1e-4)
+    def timed(exchange):
+        eng = sstg.TrainEngine(params, bn, dev)
+        trainer = Pl.DistributedTrainer(eng, exchange=exchange, max_scenes=batch) if world > 1 else None
 
-    for i in range(warmup):
-        one(i)
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for i in range(steps):
-        one(i)
-    e1.record()
-    torch.cuda.synchronize()
-    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    ms = float(ms[0])
+        def one(i):
+            n, plan, obs, pred = groups[i % len(groups)]
+            if trainer is not None:
+                trainer.step(n, obs, pred, batch, 1e-4)
+            else:
+                eng.step(plan, obs, pred, batch, 1e-4)
+
+        for i in range(warmup):
+            one(i)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            one(i)
+        e1.record()
+        torch.cuda.synchronize()
+        if trainer is not None and trainer.peer is not None:
+            trainer.peer.check()
+        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        used = trainer.exchange if trainer is not None else "none"
+        if trainer is not None and trainer.peer is not None:
+            trainer.peer.close()
+        return float(t[0]), used
+
+    ms, exchange = timed("auto")
+    nccl = None
+    if world > 1 and exchange == "peer":
+        ms_nccl, _ = timed("nccl")
+        nccl = {"value": batch * steps / (ms_nccl * 1e-3), "unit": "scenes/s", "ms_per_group": ms_nccl / steps,
+                "what": "same sharded group, exchange through one torch.distributed (NCCL) all-reduce instead"}
     peds = float(np.mean([g[0].sum() for g in groups]))
     indep = None
     if world > 1:
@@ -345,12 +360,15 @@ def run_train_leg(dev, world, rank, steps, warmup, batch=128):
         indep = {"value": world * batch * steps / (float(t2[0]) * 1e-3), "unit": "scenes/s",
                  "what": "independent trainings, one per GPU, as the reference's train.sh launches them (no collective)"}
     return {"value": batch * steps / (ms * 1e-3), "unit": "scenes/s", "ms_per_group": ms / steps, "batch": batch,
-            "independent_replicas": indep,
+            "exchange": exchange, "nccl_exchange": nccl, "independent_replicas": indep,
             "groups_timed": steps, "mean_peds_per_group": peds, "n_gpus": world,
             "what": "train(): graph build + train-mode fwd (per-scene BN stats) + NLL + full bwd + BN running stats "
                     "+ SGD, one packed ragged group of 128 ETH/UCY-shaped scenes per step (8 distinct groups cycled; a "
                     "group's working set, ~3 MB, is L2-resident by nature -- the step is latency-bound, not bandwidth-bound)"
-                    + ("; group sharded over ranks, NCCL all-reduce of the 7,563-float gradient" if world > 1 else "")}
+                    + ("; group sharded over ranks, gradient / loss / BN statistics exchanged by libsstg's peer-memory kernel "
+                       "over NVLink fused with SGD" if exchange == "peer" else
+                       "; group sharded over ranks, one NCCL all-reduce of [gradient | loss | BN statistics]"
+                       if world > 1 else "")}
 
 
 # ---------------------------------------------------------------------------------

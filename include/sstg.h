@@ -230,13 +230,48 @@ int sstg_sgd_step(float* params, const float* grad, int32_t n, float lr, float c
  *   scene_weight [S]                       1/batch_size, 0 for the unscored last scene (may be NULL = 1)
  *   ws                                     caller-owned scratch of >= sstg_train_step_workspace() floats, 16-byte aligned
  *   loss [S] per-scene NLL, grad [7563], group_loss [1] = sum_s weight[s]*loss[s] (may be NULL)
- *   graph_flags                            SSTG_GRAPH_FP64 or 0 (NORM_LAP is implied) */
+ *   graph_flags                            SSTG_GRAPH_FP64 or 0 (NORM_LAP is implied)
+ *   bn_momentum                            0.1 in the reference; NEGATIVE = leave bn[] alone (a scene-sharded
+ *                                          group applies the recurrence after the exchange, see below); the
+ *                                          statistics then stay in ws at sstg_train_step_stats_offset() floats */
 int64_t sstg_train_step_workspace(int32_t S, int32_t n_tiles, int32_t total_peds, int64_t a_floats);
+int64_t sstg_train_step_stats_offset(int32_t S, int32_t n_tiles, int32_t total_peds, int64_t a_floats);
 int sstg_train_step(const float* obs_rel, const float* pred_rel, const int32_t* seg_off, const int64_t* a_off,
                     const int32_t* tile_off, int32_t S, int32_t n_tiles, int32_t max_n, int32_t total_peds,
                     int64_t a_floats, float* params, float* bn, const float* scene_weight, float* ws,
                     int64_t ws_floats, float lr, float clip_norm, double bn_momentum, int32_t graph_flags,
                     float* loss, float* grad, float* group_loss, void* stream);
+
+/* ---- one optimiser group sharded over the GPUs of a node: gradient exchange over NVLink peer memory,
+ * fused with the optimiser step (no reference counterpart: train.py runs on one device; this is the
+ * exchange step of SURVEY 8e).  Every rank allocates one MAILBOX (sstg_peer_alloc), the 64-byte CUDA IPC
+ * handles are exchanged by the host (any transport), every rank maps the others' (sstg_peer_open).
+ * Per group each rank runs sstg_train_step(lr = 0, bn_momentum < 0) on its contiguous shard with the
+ * group's scene weights, then sstg_peer_exchange_apply, which in ONE kernel stores its gradient / loss /
+ * own statistics rows into every mailbox, signals, waits for all sources on its local flags, sums the
+ * gradients in rank order (bit-identical replicas), clips and applies SGD; the BatchNorm recurrence over the
+ * GLOBAL scene order follows on the same stream.
+ *   mailboxes [world]   HOST array of device pointers, [rank] = this rank's own mailbox
+ *   epoch               1, 2, 3, ... identical on all ranks, one per call (selects the payload parity)
+ *   max_scenes          the capacity the mailboxes were sized for (same on all ranks)
+ *   grad_local [7563], loss_local [1] (NULL = 0), stats_local [s_local,30]: this rank's contribution;
+ *   scene_lo, s_local   its scene range inside the group of s_all scenes; seg_off_all [s_all+1] (device)
+ *   grad_out [7563], loss_out [1] (may be NULL), stats_out [s_all,30]: the reduced group quantities
+ *   status [1] int32    device word, 0 on success; 1+r if source r had not delivered within timeout_ns
+ *                       (0 = 5 s): then nothing is applied -- the kernel never spins unbounded */
+#define SSTG_MAX_RANKS 8
+#define SSTG_PEER_HANDLE_BYTES 64
+int64_t sstg_peer_mailbox_bytes(int32_t world, int32_t max_scenes);
+int sstg_peer_alloc(int64_t bytes, void** ptr, unsigned char* handle);
+int sstg_peer_open(const unsigned char* handle, void** ptr);
+int sstg_peer_close(void* ptr);
+int sstg_peer_free(void* ptr);
+int sstg_peer_exchange_apply(void* const* mailboxes, int32_t world, int32_t rank, uint32_t epoch,
+                             int32_t max_scenes, const float* grad_local, const float* loss_local,
+                             const float* stats_local, int32_t scene_lo, int32_t s_local,
+                             const int32_t* seg_off_all, int32_t s_all, float* params, float* bn, float lr,
+                             float clip_norm, double bn_momentum, float* grad_out, float* loss_out,
+                             float* stats_out, int32_t* status, uint64_t timeout_ns, void* stream);
 
 #ifdef __cplusplus
 }

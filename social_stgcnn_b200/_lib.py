@@ -47,6 +47,14 @@ _SIGS.update({
     "sstg_stgcn_forward_fused": (C.c_int, [_p, _p, _i32, _i32, _p, _p, _p, _p, _p]),
     "sstg_decode_tracks": (C.c_int, [_p, _p, _i32, _p, _p, _p, _p]),
     "sstg_sgd_step": (C.c_int, [_p, _p, _i32, _f32, _f32, _p, _p]),
+    "sstg_train_step_stats_offset": (C.c_int64, [_i32, _i32, _i32, _i64]),
+    "sstg_peer_mailbox_bytes": (C.c_int64, [_i32, _i32]),
+    "sstg_peer_alloc": (C.c_int, [_i64, C.POINTER(C.c_void_p), C.c_char_p]),
+    "sstg_peer_open": (C.c_int, [C.c_char_p, C.POINTER(C.c_void_p)]),
+    "sstg_peer_close": (C.c_int, [_p]),
+    "sstg_peer_free": (C.c_int, [_p]),
+    "sstg_peer_exchange_apply": (C.c_int, [C.POINTER(C.c_void_p), _i32, _i32, C.c_uint32, _i32, _p, _p, _p, _i32, _i32,
+                                           _p, _i32, _p, _p, _f32, _f32, _f64, _p, _p, _p, _p, C.c_uint64, _p]),
 })
 
 _lock = threading.Lock()

@@ -16,7 +16,7 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 OBJ = os.path.join(PKG, "build")
 LIB = os.path.join(PKG, "libsstg.so")
-SOURCES = ["graph_build.cu", "stgcn_fwd.cu", "txpcnn_fwd.cu", "eval_kernels.cu", "train_kernels.cu", "txpcnn_bwd.cu", "stgcn_fused.cu", "txpcnn_wino.cu", "sstg_api.cu"]
+SOURCES = ["graph_build.cu", "stgcn_fwd.cu", "txpcnn_fwd.cu", "eval_kernels.cu", "train_kernels.cu", "txpcnn_bwd.cu", "stgcn_fused.cu", "txpcnn_wino.cu", "peer_exchange.cu", "sstg_api.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC",

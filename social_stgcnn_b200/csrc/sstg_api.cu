@@ -293,6 +293,11 @@ int64_t sstg_train_step_workspace(int32_t S, int32_t n_tiles, int32_t total_peds
   return train_ws_layout(S, n_tiles, total_peds, a_floats).total;
 }
 
+int64_t sstg_train_step_stats_offset(int32_t S, int32_t n_tiles, int32_t total_peds, int64_t a_floats) {
+  if (S < 0 || n_tiles < 0 || total_peds < 0 || a_floats < 0) return SSTG_EINVAL;
+  return train_ws_layout(S, n_tiles, total_peds, a_floats).stats;
+}
+
 int sstg_train_step(const float* obs_rel, const float* pred_rel, const int32_t* seg_off, const int64_t* a_off,
                     const int32_t* tile_off, int32_t S, int32_t n_tiles, int32_t max_n, int32_t total_peds,
                     int64_t a_floats, float* params, float* bn, const float* scene_weight, float* ws,
@@ -301,8 +306,12 @@ int sstg_train_step(const float* obs_rel, const float* pred_rel, const int32_t* 
   if (S < 0 || n_tiles < 0 || total_peds < 0 || a_floats < 0 || (S > 0 && max_n < 1)) return SSTG_EINVAL;
   if (max_n > SSTG_MAX_PEDS) return SSTG_ETOOBIG;
   if (!params || !bn || !grad || !loss) return SSTG_EINVAL;
-  if (S == 0) return sstg_backward(nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0, 1, 0, nullptr, nullptr, nullptr,
-                                   nullptr, nullptr, nullptr, nullptr, grad, stream);
+  if (S == 0) {
+    if (group_loss)
+      SSTG_CUDA_TRY(cudaMemsetAsync(group_loss, 0, sizeof(float), static_cast<cudaStream_t>(stream)), "loss memset");
+    return sstg_backward(nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0, 1, 0, nullptr, nullptr, nullptr, nullptr,
+                         nullptr, nullptr, nullptr, grad, stream);
+  }
   if (!obs_rel || !pred_rel || !seg_off || !a_off || !tile_off || !ws || !aligned16(ws)) return SSTG_EINVAL;
   const TrainWs w = train_ws_layout(S, n_tiles, total_peds, a_floats);
   if (ws_floats < w.total) return SSTG_EINVAL;
@@ -319,8 +328,10 @@ int sstg_train_step(const float* obs_rel, const float* pred_rel, const int32_t* 
   rc = sstg_backward(ws + w.V, ws + w.A, seg_off, a_off, tile_off, S, n_tiles, max_n, total_peds, params, ws + w.save,
                      ws + w.stats, ws + w.dvp, ws + w.dH, ws + w.pst, ws + w.ptx, grad, stream);
   if (rc) return rc;
-  rc = sstg_bn_running_update(ws + w.stats, seg_off, S, bn_momentum, bn, stream);
-  if (rc) return rc;
+  if (bn_momentum >= 0.0) {  // negative: the caller applies the recurrence itself (scene-sharded groups)
+    rc = sstg_bn_running_update(ws + w.stats, seg_off, S, bn_momentum, bn, stream);
+    if (rc) return rc;
+  }
   if (group_loss) {
     rc = launch_group_loss(loss, scene_weight, S, group_loss, static_cast<cudaStream_t>(stream));
     if (rc) return rc;

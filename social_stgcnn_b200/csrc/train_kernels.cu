@@ -581,7 +581,9 @@ nll_fwd_bwd_kernel(const float* __restrict__ Vpred, const float* __restrict__ Vt
 constexpr int BN_TILE = 128;  // scenes staged per pass (128 x 30 doubles = 30 KB of static shared memory)
 __global__ void __launch_bounds__(256)
 bn_running_update_kernel(const float* __restrict__ stats, const int32_t* __restrict__ seg_off, int S,
-                         double momentum, float* __restrict__ bn) {
+                         double momentum, float* __restrict__ bn, const int32_t* __restrict__ abort_flag) {
+  // a failed peer exchange (peer_exchange.cu) leaves the statistics undefined: leave the buffers alone
+  if (abort_flag && *abort_flag) return;
   // The recurrence is sequential in the scene index, but its inputs are not: 256 threads stage a
   // tile of per-scene statistics (and element counts) in shared memory with coalesced loads, then
   // 30 threads run the recurrence over the tile out of shared memory.
@@ -736,9 +738,9 @@ int launch_nll_fwd_bwd(const float* Vpred, const float* Vtr, const int32_t* seg_
 }
 
 int launch_bn_running_update(const float* stats, const int32_t* seg_off, int S, double momentum, float* bn,
-                             cudaStream_t st) {
+                             cudaStream_t st, const int32_t* abort_flag) {
   if (S == 0) return SSTG_OK;
-  bn_running_update_kernel<<<1, 256, 0, st>>>(stats, seg_off, S, momentum, bn);
+  bn_running_update_kernel<<<1, 256, 0, st>>>(stats, seg_off, S, momentum, bn, abort_flag);
   SSTG_CUDA_TRY(cudaGetLastError(), "bn_running_update launch");
   return SSTG_OK;
 }

@@ -685,6 +685,38 @@ class TrainEngine:
         self.last_loss = loss[:plan.S]
         return loss[plan.S]
 
+    def shard_forward_backward(self, plan: Optional[ScenePlan], obs_rel, pred_rel, scene_weight, *,
+                               graph_fp64: bool = False):
+        """This rank's part of a scene-sharded optimiser group in one library call (sstg_train_step with
+        lr = 0 and the BN recurrence deferred): returns device pointers-as-tensors (grad_local[7563],
+        weighted loss[1], scene_stats[S,30]) for PeerExchange.exchange.  `plan` None = empty shard."""
+        dev = self.device
+        gl = self._ws.get("grad_local")
+        if gl is None:
+            gl = self._ws["grad_local"] = torch.zeros(L.N_PARAMS + 1, dtype=torch.float32, device=dev)
+        if plan is None or plan.S == 0:
+            gl.zero_()
+            return gl, gl[L.N_PARAMS:], None
+        dp = plan.on(dev)
+        _need(obs_rel, torch.float32, "obs_rel", dev)
+        _need(pred_rel, torch.float32, "pred_rel", dev)
+        _need(scene_weight, torch.float32, "scene_weight", dev)
+        if tuple(obs_rel.shape) != (plan.P, 2, L.T_OBS) or tuple(pred_rel.shape) != (plan.P, 2, L.T_PRED):
+            raise ValueError(f"obs_rel / pred_rel must be [{plan.P}, 2, 8] / [{plan.P}, 2, 12]")
+        if scene_weight.numel() != plan.S:
+            raise ValueError("scene_weight must hold one weight per scene of the shard")
+        ws, need, loss, _ = self._step_buffers(plan, 1)
+        lib = L.load()
+        off = int(lib.sstg_train_step_stats_offset(plan.S, plan.n_tiles, plan.P, plan.a_floats))
+        with torch.cuda.device(dev):
+            L.check(lib.sstg_train_step(
+                _ptr(obs_rel), _ptr(pred_rel), _ptr(dp.seg_off), _ptr(dp.a_off), _ptr(dp.tile_off), plan.S,
+                plan.n_tiles, plan.max_n, plan.P, plan.a_floats, _ptr(self.params), _ptr(self.bn), _ptr(scene_weight),
+                _ptr(ws), need, 0.0, 0.0, -1.0, L.GRAPH_FP64 if graph_fp64 else 0,
+                _ptr(loss), _ptr(gl), gl.data_ptr() + 4 * L.N_PARAMS, _stream(dev)), "sstg_train_step")
+        self.last_loss = loss[:plan.S]
+        return gl, gl[L.N_PARAMS:], ws[off:off + plan.S * L.N_BN].view(plan.S, L.N_BN)
+
     def step_unfused(self, plan: ScenePlan, obs_rel, pred_rel, batch_size: int, lr: float, clip_grad=None,
              *, graph_fp64: bool = True):
         """One optimiser group: returns the group loss (sum_i w_i * l_i) as a 0-dim device tensor."""

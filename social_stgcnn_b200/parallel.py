@@ -151,38 +151,216 @@ class ShardedEvaluator:
         return reduce_scores(r["min_ade"].sum(), r["min_fde"].sum(), plan.P, self.group, dev)
 
 
+class PeerExchange:
+    """The mailboxes of sstg_peer_exchange_apply (include/sstg.h) for one rank: its own mailbox in HBM
+    plus the CUDA-IPC mappings of every other rank's.  The 64-byte handles travel through
+    torch.distributed (plumbing); the exchange itself is libsstg.so's kernel storing over NVLink.
+
+    All ranks must sit on one node (NVLink/NVSwitch peer access) and call `exchange` in lockstep."""
+
+    def __init__(self, device, max_scenes: int = 256, group=None, timeout_s: float = 5.0, *, _shared=None):
+        import ctypes as C
+        lib = L.load()
+        self.device = torch.device(device)
+        self.group, self.max_scenes, self.epoch = group, int(max_scenes), 0
+        self.timeout_ns = int(timeout_s * 1e9)
+        self._own, self._opened = None, []
+        if _shared is not None:                      # several ranks emulated inside one process (tests)
+            self.world, self.rank, ptrs = _shared
+        else:
+            self.world, self.rank = _world(group)
+            nbytes = int(lib.sstg_peer_mailbox_bytes(self.world, self.max_scenes))
+            if nbytes < 0:
+                L.check(nbytes, "sstg_peer_mailbox_bytes")
+            own, handle = C.c_void_p(), C.create_string_buffer(64)
+            with torch.cuda.device(self.device):
+                L.check(lib.sstg_peer_alloc(nbytes, C.byref(own), handle), "sstg_peer_alloc")
+            self._own = own.value
+            import socket
+            mine = (socket.gethostname(), handle.raw)
+            everyone = [None] * self.world
+            if self.world > 1:
+                dist.all_gather_object(everyone, mine, group=group)
+            else:
+                everyone = [mine]
+            if any(h[0] != mine[0] for h in everyone):
+                raise RuntimeError("PeerExchange needs all ranks on one node (peer memory over NVLink)")
+            ptrs = []
+            for r, (_, raw) in enumerate(everyone):
+                if r == self.rank:
+                    ptrs.append(self._own)
+                    continue
+                q = C.c_void_p()
+                with torch.cuda.device(self.device):
+                    L.check(lib.sstg_peer_open(raw, C.byref(q)), f"sstg_peer_open(rank {r})")
+                self._opened.append(q.value)
+                ptrs.append(q.value)
+            if self.world > 1:
+                torch.cuda.synchronize(self.device)
+                dist.barrier(group=group)            # nobody stores into a mailbox that is not mapped and zeroed yet
+        self._boxes = (C.c_void_p * self.world)(*ptrs)
+        self.status = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self.loss = torch.zeros(1, dtype=torch.float32, device=self.device)
+        self.stats = torch.zeros(max(self.max_scenes, 1), L.N_BN, dtype=torch.float32, device=self.device)
+
+    @classmethod
+    def local_group(cls, world: int, max_scenes: int, device, timeout_s: float = 5.0):
+        """`world` exchanges that live in THIS process on one GPU (each rank's kernel goes on its own
+        stream): the protocol, runnable on a single-GPU box."""
+        import ctypes as C
+        lib = L.load()
+        device = torch.device(device)
+        nbytes = int(lib.sstg_peer_mailbox_bytes(world, max_scenes))
+        if nbytes < 0:
+            L.check(nbytes, "sstg_peer_mailbox_bytes")
+        ptrs = []
+        for _ in range(world):
+            q, h = C.c_void_p(), C.create_string_buffer(64)
+            with torch.cuda.device(device):
+                L.check(lib.sstg_peer_alloc(nbytes, C.byref(q), h), "sstg_peer_alloc")
+            ptrs.append(q.value)
+        out = [cls(device, max_scenes, None, timeout_s, _shared=(world, r, ptrs)) for r in range(world)]
+        out[0]._owned_all = ptrs
+        return out
+
+    def exchange(self, engine, grad_local, loss_local, stats_local, scene_lo: int, s_local: int, seg_off_all,
+                 s_all: int, lr: float, clip_norm: float = 0.0, bn_momentum: float = 0.1, stream=None):
+        """Push this rank's contribution, wait for all, apply SGD + the BN recurrence to `engine`
+        (params / bn / grad in place).  Asynchronous: `check()` reports a peer that never arrived."""
+        if s_all > self.max_scenes:
+            raise ValueError(f"group of {s_all} scenes exceeds the mailbox capacity {self.max_scenes}")
+        self.epoch += 1
+        ptr = lambda t: t.data_ptr() if isinstance(t, torch.Tensor) else (t or None)
+        if stream is None:
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+        with torch.cuda.device(self.device):
+            L.check(L.load().sstg_peer_exchange_apply(
+                self._boxes, self.world, self.rank, self.epoch, self.max_scenes, ptr(grad_local), ptr(loss_local),
+                ptr(stats_local), int(scene_lo), int(s_local), ptr(seg_off_all), int(s_all), engine.params.data_ptr(),
+                engine.bn.data_ptr(), float(lr), float(clip_norm or 0.0), float(bn_momentum), engine.grad.data_ptr(),
+                self.loss.data_ptr(), self.stats.data_ptr(), self.status.data_ptr(), self.timeout_ns, stream),
+                "sstg_peer_exchange_apply")
+        return self.loss[0]
+
+    def check(self):
+        """Synchronise and raise if any exchange since the last check timed out."""
+        st = int(self.status.item())
+        if st:
+            raise RuntimeError(f"peer exchange: rank {st - 1} did not deliver within {self.timeout_ns / 1e9:.1f} s "
+                               f"(this is rank {self.rank}); weights were left untouched")
+
+    def close(self):
+        lib = L.load()
+        with torch.cuda.device(self.device):
+            torch.cuda.synchronize(self.device)
+            for q in self._opened:
+                lib.sstg_peer_close(q)
+            self._opened = []
+            for q in getattr(self, "_owned_all", []) or ([self._own] if self._own else []):
+                lib.sstg_peer_free(q)
+            self._own, self._owned_all = None, []
+
+
+class _ShardedGroup:
+    """Host metadata of one optimiser group as this rank sees it (cached per pedestrian-count vector)."""
+
+    def __init__(self, n_peds, batch_size, world, rank, dev):
+        from . import engine as E
+        self.n_peds = n_peds
+        self.S_all = int(n_peds.size)
+        self.lo, self.hi = shard_bounds(n_peds, world)[rank]
+        seg = np.concatenate([[0], np.cumsum(n_peds)]).astype(np.int64)
+        self.p_lo, self.p_hi = int(seg[self.lo]), int(seg[self.hi])
+        self.w_all = E.group_weights(self.S_all, batch_size)
+        self.plan = E.ScenePlan(n_peds[self.lo:self.hi]) if self.hi > self.lo else None
+        self.w_dev = torch.from_numpy(np.ascontiguousarray(self.w_all[self.lo:self.hi])).to(dev) \
+            if self.plan is not None else None
+        self.seg_all_dev = torch.from_numpy(seg.astype(np.int32)).to(dev)
+        self.full_plan = None
+
+
 class DistributedTrainer:
     """One optimiser group of train() (train.py:28-79) spread over the ranks of `group`.
 
     Every rank holds identical weights and BN buffers (a TrainEngine).  `step` takes the
     WHOLE group (all ranks pass the same n_peds / tensors, or each its own slice with
     `presliced=True`), runs graph build + train-mode forward + backward on this rank's
-    contiguous shard with the group's loss weights, all-reduces the flat gradient, gathers
-    the BN statistics, and applies the identical SGD step everywhere."""
+    contiguous shard with the group's loss weights, exchanges gradient / loss / BN statistics and
+    applies the identical SGD step and BN recurrence everywhere.
 
-    def __init__(self, engine, group=None):
+    exchange = "peer": libsstg.so's one-kernel exchange over NVLink peer memory (PeerExchange), fused
+                       with the SGD step -- two library calls per group, no torch op in between;
+               "nccl": one torch.distributed all-reduce of [gradient | loss | statistics rows];
+               "auto": "peer" when every rank is on CUDA on one node and world <= 8 (env
+                       SSTG_EXCHANGE=nccl|peer overrides), else "nccl"."""
+
+    def __init__(self, engine, group=None, exchange: str = "auto", max_scenes: int = 256, *, _emulate=None):
+        import os
         self.engine, self.group = engine, group
-        self._flat = {}
+        self._flat, self._groups = {}, {}
+        self._wr = None
+        if _emulate is not None:       # a PeerExchange.local_group member: several ranks inside one process (tests)
+            self.peer, self.exchange = _emulate, "peer"
+            self._wr = (_emulate.world, _emulate.rank)
+            return
+        world, _ = _world(group)
+        mode = os.environ.get("SSTG_EXCHANGE", exchange)
+        if mode not in ("auto", "peer", "nccl"):
+            raise ValueError("exchange must be auto, peer or nccl")
+        self.peer = None
+        if world > 1 and world <= 8 and (mode == "peer" or (mode == "auto" and engine.device.type == "cuda")):
+            try:
+                self.peer = PeerExchange(engine.device, max_scenes, group)
+                ok = 1
+            except Exception as e:
+                if mode == "peer":
+                    raise
+                import warnings
+                warnings.warn(f"peer-memory exchange unavailable ({e}); using the NCCL all-reduce")
+                ok = 0
+            t = torch.tensor([ok], dtype=torch.int32, device=engine.device)
+            dist.all_reduce(t, op=dist.ReduceOp.MIN, group=group)
+            if int(t[0]) == 0 and self.peer is not None:
+                self.peer.close()
+                self.peer = None
+        self.exchange = "peer" if self.peer is not None else ("nccl" if world > 1 else "none")
+
+    def _group(self, n_peds, batch_size):
+        key = (n_peds.tobytes(), batch_size)
+        g = self._groups.get(key)
+        if g is None:
+            if len(self._groups) >= 256:
+                self._groups.clear()
+            world, rank = self._wr or _world(self.group)
+            g = self._groups[key] = _ShardedGroup(n_peds, batch_size, world, rank, self.engine.device)
+        return g
 
     def step(self, n_peds, obs_rel, pred_rel, batch_size: int, lr: float, clip_grad: Optional[float] = None,
-             presliced: bool = False):
+             presliced: bool = False, graph_fp64: bool = False):
         from . import engine as E
-        world, rank = _world(self.group)
-        n_peds = np.asarray(n_peds, np.int32).reshape(-1)
-        bounds = shard_bounds(n_peds, world)
-        lo, hi = bounds[rank]
-        seg = np.concatenate([[0], np.cumsum(n_peds)])
+        world, rank = self._wr or _world(self.group)
+        n_peds = np.ascontiguousarray(np.asarray(n_peds, np.int32).reshape(-1))
+        g = self._group(n_peds, batch_size)
+        lo, hi = g.lo, g.hi
         eng, dev = self.engine, self.engine.device
-        w_all = E.group_weights(int(n_peds.size), batch_size)
-        loss_local = torch.zeros(1, dtype=torch.float64, device=dev)
+        o = p = None
         if hi > lo:
-            plan = E.ScenePlan(n_peds[lo:hi])
             if presliced:
                 o, p = obs_rel, pred_rel
             else:
-                o = torch.as_tensor(obs_rel)[seg[lo]:seg[hi]].to(dev).contiguous()
-                p = torch.as_tensor(pred_rel)[seg[lo]:seg[hi]].to(dev).contiguous()
-            r = eng.forward_backward(plan, o, p, w_all[lo:hi])
+                o = torch.as_tensor(obs_rel)[g.p_lo:g.p_hi].to(dev).contiguous()
+                p = torch.as_tensor(pred_rel)[g.p_lo:g.p_hi].to(dev).contiguous()
+        if self.peer is not None:
+            # library call 1: this shard's graph build + forward + backward (no update);
+            # library call 2: exchange over peer memory + SGD + BN recurrence in global scene order
+            grad_l, loss_l, stats_l = eng.shard_forward_backward(g.plan, o, p, g.w_dev, graph_fp64=graph_fp64)
+            out = self.peer.exchange(eng, grad_l, loss_l, stats_l, lo, hi - lo, g.seg_all_dev, g.S_all, lr,
+                                     clip_grad or 0.0)
+            eng.num_batches_tracked += g.S_all
+            return out
+        loss_local = torch.zeros(1, dtype=torch.float64, device=dev)
+        if hi > lo:
+            r = eng.forward_backward(g.plan, o, p, g.w_dev, graph_fp64=graph_fp64)
             stats = r["scene_stats"]
             loss_local += (r["loss"].double() * r["weight"].double()).sum()
         else:
@@ -191,7 +369,7 @@ class DistributedTrainer:
         # ONE collective per optimiser group: [gradient 7563 | group loss 1 | per-scene BN statistics S x 30]
         # in a single flat buffer, all-reduced (sum).  Every rank fills only its own scenes' rows of the
         # statistics block, so the sum IS the concatenation in global scene order.
-        S_all = int(n_peds.size)
+        S_all = g.S_all
         if world > 1:
             flat = self._flat.get(S_all)
             if flat is None:
@@ -208,8 +386,9 @@ class DistributedTrainer:
             stats_all = st
         else:
             stats_all = stats
-        full = E.ScenePlan(n_peds)
-        E.bn_running_update(full.on(dev), stats_all.contiguous(), eng.bn)
-        eng.num_batches_tracked += int(n_peds.size)
+        if g.full_plan is None:
+            g.full_plan = E.ScenePlan(n_peds)
+        E.bn_running_update(g.full_plan.on(dev), stats_all.contiguous(), eng.bn)
+        eng.num_batches_tracked += S_all
         E.sgd_step(eng.params, eng.grad, lr, clip_grad or 0.0)
         return loss_local[0]

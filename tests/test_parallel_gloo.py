@@ -70,7 +70,7 @@ class _FakeEngine:
         self.num_batches_tracked = 0
         self.seen = []
 
-    def forward_backward(self, plan, obs_rel, pred_rel, weight):
+    def forward_backward(self, plan, obs_rel, pred_rel, weight, **kw):
         ids = obs_rel[:, 0, 0].long()                      # pedestrian rows carry their global scene id
         first = torch.unique_consecutive(ids)
         self.seen = first.tolist()
