@@ -305,7 +305,7 @@ int sstg_train_step(const float* obs_rel, const float* pred_rel, const int32_t* 
                     float* loss, float* grad, float* group_loss, void* stream) {
   if (S < 0 || n_tiles < 0 || total_peds < 0 || a_floats < 0 || (S > 0 && max_n < 1)) return SSTG_EINVAL;
   if (max_n > SSTG_MAX_PEDS) return SSTG_ETOOBIG;
-  if (!params || !bn || !grad || !loss) return SSTG_EINVAL;
+  if (!params || !bn || !grad || !loss || !(bn_momentum <= 1.0)) return SSTG_EINVAL;
   if (S == 0) {
     if (group_loss)
       SSTG_CUDA_TRY(cudaMemsetAsync(group_loss, 0, sizeof(float), static_cast<cudaStream_t>(stream)), "loss memset");
@@ -325,18 +325,25 @@ int sstg_train_step(const float* obs_rel, const float* pred_rel, const int32_t* 
   if (rc) return rc;
   rc = sstg_nll_backward(ws + w.vp, ws + w.Vtr, seg_off, S, scene_weight, loss, ws + w.dvp, stream);
   if (rc) return rc;
-  rc = sstg_backward(ws + w.V, ws + w.A, seg_off, a_off, tile_off, S, n_tiles, max_n, total_peds, params, ws + w.save,
-                     ws + w.stats, ws + w.dvp, ws + w.dH, ws + w.pst, ws + w.ptx, grad, stream);
-  if (rc) return rc;
-  if (bn_momentum >= 0.0) {  // negative: the caller applies the recurrence itself (scene-sharded groups)
-    rc = sstg_bn_running_update(ws + w.stats, seg_off, S, bn_momentum, bn, stream);
+  // backward without its own gradient reduction: the reduction, the BN recurrence, the group loss and
+  // (without clipping) the SGD update share ONE launch
+  {
+    const long long P = total_peds;
+    const float* save = ws + w.save;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    rc = launch_txpcnn_backward(ws + w.dvp, save + P * 120, save + P * 360, P * 60, save + P * 80, seg_off, tile_off,
+                                n_tiles, max_n, params, ws + w.dH, ws + w.ptx, st);
     if (rc) return rc;
-  }
-  if (group_loss) {
-    rc = launch_group_loss(loss, scene_weight, S, group_loss, static_cast<cudaStream_t>(stream));
+    rc = launch_stgcn_train_backward(ws + w.V, ws + w.A, seg_off, a_off, S, max_n, params, save, save + P * 40,
+                                     ws + w.stats, ws + w.dH, ws + w.pst, st);
     if (rc) return rc;
+    const bool clip = clip_norm > 0.f;
+    rc = launch_train_tail(ws + w.pst, stgcn_train_bwd_rows(S), ws + w.ptx, txpcnn_bwd_rows(n_tiles),
+                           SSTG_TXP_GRAD_STRIDE, grad, params, clip ? 0.f : lr, ws + w.stats, seg_off, S, bn_momentum,
+                           bn, loss, scene_weight, group_loss, st);
+    if (rc) return rc;
+    if (clip && lr != 0.f) rc = sstg_sgd_step(params, grad, SSTG_N_PARAMS, lr, clip_norm, nullptr, stream);
   }
-  if (lr != 0.f) rc = sstg_sgd_step(params, grad, SSTG_N_PARAMS, lr, clip_norm, nullptr, stream);
   return rc;
 }
 

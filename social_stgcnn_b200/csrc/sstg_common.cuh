@@ -146,6 +146,10 @@ int launch_bn_running_update(const float* stats, const int32_t* seg_off, int S, 
 int launch_grad_finalize(const float* part_st, int rows_st, const float* part_tx, int rows_tx, int tx_stride,
                          float* grad, cudaStream_t st);
 int launch_group_loss(const float* loss, const float* weight, int S, float* out, cudaStream_t st);
+int launch_train_tail(const float* part_st, int rows_st, const float* part_tx, int rows_tx, int tx_stride,
+                      float* grad, float* params, float lr, const float* stats, const int32_t* seg_off, int S,
+                      double momentum, float* bn, const float* loss, const float* weight, float* group_loss,
+                      cudaStream_t st);
 int launch_sgd_step(float* params, const float* grad, int n, float lr, float clip_norm, float* grad_norm_out,
                     cudaStream_t st);
 int launch_nll_forward(const float* Vpred, const float* Vtr, const int32_t* seg_off, int S, float* loss,

@@ -134,6 +134,7 @@ stgcn_train_fwd_kernel(const float* __restrict__ V, const float* __restrict__ A,
 #pragma unroll
       for (int j = 0; j < NJ; ++j) y[c][j] = 0.f;
     const float* At = A + a_off[s] + static_cast<size_t>(t) * N * N;
+#pragma unroll 8
     for (int v = 0; v < N; ++v) {
       const float4 g4 = *reinterpret_cast<const float4*>(gw + v * 8);
       const float g5 = gw[v * 8 + 4];
@@ -308,7 +309,7 @@ stgcn_train_bwd_kernel(const float* __restrict__ V, const float* __restrict__ A,
 
   // per-thread gradient partials carried over all scenes of this CTA
   float dWr[C][2], dbr[C], dW2[C][C][3], db2[C], da1 = 0.f, da2 = 0.f;
-  float dWg[C][2], dbg[C];  // warp-uniform (every lane holds the warp's value)
+  float dWg[C][2], dbg[C];  // per lane (lane <-> source node), warp-summed once at the end
 #pragma unroll
   for (int c = 0; c < C; ++c) {
     dWr[c][0] = dWr[c][1] = dbr[c] = db2[c] = dWg[c][0] = dWg[c][1] = dbg[c] = 0.f;
@@ -443,23 +444,37 @@ stgcn_train_bwd_kernel(const float* __restrict__ V, const float* __restrict__ A,
       }
     }
     __syncwarp();
-    // ---- phase E: d_g[c, t, v] = sum_w d_y[c, t, w] A[t, v, w];  dWg, dbg
+    // ---- phase E: d_g[c, t, v] = sum_w d_y[c, t, w] A[t, v, w];  dWg, dbg.
+    // Lanes <-> source nodes v, each lane walks ITS row of A (w ascending, 4 loads in flight) against
+    // d_y broadcast from shared memory: no cross-lane reduction and no load->shuffle chain per node --
+    // the per-node latency chain was what set the duration of a small group.  A[t] is at most 16 KB per
+    // warp at N = 64 and stays in L1 across the strided row walk.
     const float* At = A + a_off[s] + static_cast<size_t>(t) * N * N;
-    for (int v = 0; v < N; ++v) {
+    const float* dyt = dq + t * NP;
+    for (int v = lane; v < N; v += 32) {
       const float* row = At + static_cast<size_t>(v) * N;
       float pg[C] = {0.f, 0.f, 0.f, 0.f, 0.f};
-      for (int k = lane; k < N; k += 32) {
-        const float a = row[k];
+      int w = 0;
+      for (; w + 4 <= N; w += 4) {
+        float a[4];
 #pragma unroll
-        for (int c = 0; c < C; ++c) pg[c] = fmaf(dq[(c * T_OBS + t) * NP + k], a, pg[c]);
+        for (int j = 0; j < 4; ++j) a[j] = __ldg(row + w + j);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+          for (int c = 0; c < C; ++c) pg[c] = fmaf(dyt[c * T_OBS * NP + w + j], a[j], pg[c]);
+      }
+      for (; w < N; ++w) {
+        const float a = __ldg(row + w);
+#pragma unroll
+        for (int c = 0; c < C; ++c) pg[c] = fmaf(dyt[c * T_OBS * NP + w], a, pg[c]);
       }
       const float2 vv = vp[v];
 #pragma unroll
       for (int c = 0; c < C; ++c) {
-        const float dg = warp_sum(pg[c]);
-        dWg[c][0] = fmaf(dg, vv.x, dWg[c][0]);
-        dWg[c][1] = fmaf(dg, vv.y, dWg[c][1]);
-        dbg[c] += dg;
+        dWg[c][0] = fmaf(pg[c], vv.x, dWg[c][0]);
+        dWg[c][1] = fmaf(pg[c], vv.y, dWg[c][1]);
+        dbg[c] += pg[c];
       }
     }
     __syncthreads();  // pb / dz / dq are rewritten by the next scene
@@ -487,7 +502,13 @@ stgcn_train_bwd_kernel(const float* __restrict__ V, const float* __restrict__ A,
     v1[i++] = da1;
     v1[i++] = da2;
     block_sum<97>(v1, red);
-    // warp-uniform dWg/dbg: sum over warps through shared
+    // dWg/dbg: lanes, then warps in ascending order through shared
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      dWg[c][0] = warp_sum(dWg[c][0]);
+      dWg[c][1] = warp_sum(dWg[c][1]);
+      dbg[c] = warp_sum(dbg[c]);
+    }
     if (lane == 0) {
 #pragma unroll
       for (int c = 0; c < C; ++c) {
@@ -523,55 +544,71 @@ stgcn_train_bwd_kernel(const float* __restrict__ V, const float* __restrict__ A,
 }
 
 // ---------------------------------------------------------------------------------------
-// NLL forward + gradient w.r.t. V_pred, one warp per scene (metrics.py:84-113).
+// NLL forward + gradient w.r.t. V_pred (metrics.py:84-113): one CTA per scene, warp t <-> predicted
+// timestep t, lanes <-> pedestrians -- an optimiser group is ~128 small scenes, so the kernel is
+// latency-bound and the longest scene sets its duration; 12 warps cut that chain 12-fold.
 //   loss[s]  = mean over the 12*N_s elements of -log(max(pdf, 1e-20))
 //   dVpred   = weight[s] / (12 N_s) * d(-log pdf)/dV_pred      (zero where the clamp is active)
+// The scene sum is taken per warp, then over the 12 warps in ascending order (fixed order).
 // ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
+constexpr int NLL_THREADS = T_PRED * 32;
+__global__ void __launch_bounds__(NLL_THREADS)
 nll_fwd_bwd_kernel(const float* __restrict__ Vpred, const float* __restrict__ Vtr,
                    const int32_t* __restrict__ seg_off, int S, const float* __restrict__ weight,
                    float* __restrict__ loss, float* __restrict__ dV) {
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (warp >= S) return;
-  const int n0 = seg_off[warp], N = seg_off[warp + 1] - n0;
-  const float* vp = Vpred + static_cast<size_t>(n0) * 60;
-  float* dv = dV + static_cast<size_t>(n0) * 60;
-  const float2* vt = reinterpret_cast<const float2*>(Vtr) + static_cast<size_t>(n0) * T_PRED;
-  const int tot = T_PRED * N;
-  const float wgt = (weight != nullptr ? weight[warp] : 1.f) / static_cast<float>(tot);
-  float sum = 0.f;
-  for (int i = lane; i < tot; i += 32) {
-    const float2 tr = vt[i];
-    const float nx = tr.x - vp[i];
-    const float ny = tr.y - vp[12 * N + i];
-    const float sx = expf(vp[24 * N + i]);
-    const float sy = expf(vp[36 * N + i]);
-    const float rho = tanhf(vp[48 * N + i]);
-    const float sxsy = sx * sy;
-    const float qx = nx / sx, qy = ny / sy;
-    const float cross = __fdiv_rn(__fmul_rn(__fmul_rn(rho, nx), ny), sxsy);
-    const float z = __fsub_rn(__fadd_rn(__fmul_rn(qx, qx), __fmul_rn(qy, qy)), __fmul_rn(2.f, cross));
-    const float q = __fsub_rn(1.f, __fmul_rn(rho, rho));
-    float pdf = expf(__fdiv_rn(-z, __fmul_rn(2.f, q)));
-    pdf = __fdiv_rn(pdf, __fmul_rn(6.283185307179586f, __fmul_rn(sxsy, sqrtf(q))));
-    sum += -logf(fmaxf(pdf, 1e-20f));
-    float g0 = 0.f, g1 = 0.f, g2 = 0.f, g3 = 0.f, g4 = 0.f;
-    if (pdf >= 1e-20f) {  // torch.clamp passes the gradient where input >= min
-      const float iq = 1.f / q;
-      g0 = -(qx / sx - rho * qy / sx) * iq;
-      g1 = -(qy / sy - rho * qx / sy) * iq;
-      g2 = 1.f - (qx * qx - cross) * iq;
-      g3 = 1.f - (qy * qy - cross) * iq;
-      g4 = -(nx * ny) / sxsy + z * rho * iq - rho;
+  __shared__ float part[T_PRED];
+  const int t = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int s = blockIdx.x; s < S; s += gridDim.x) {
+    const int n0 = seg_off[s], N = seg_off[s + 1] - n0;
+    const float* vp = Vpred + static_cast<size_t>(n0) * 60;
+    float* dv = dV + static_cast<size_t>(n0) * 60;
+    const float2* vt = reinterpret_cast<const float2*>(Vtr) + static_cast<size_t>(n0) * T_PRED;
+    const int tot = T_PRED * N;
+    const float wgt = (weight != nullptr ? weight[s] : 1.f) / static_cast<float>(tot);
+    float sum = 0.f;
+    for (int n = lane; n < N; n += 32) {
+      const int i = t * N + n;
+      const float2 tr = vt[i];
+      const float m0 = vp[i], m1 = vp[12 * N + i], l2 = vp[24 * N + i], l3 = vp[36 * N + i], l4 = vp[48 * N + i];
+      const float nx = tr.x - m0;
+      const float ny = tr.y - m1;
+      const float sx = expf(l2);
+      const float sy = expf(l3);
+      const float rho = tanhf(l4);
+      const float sxsy = sx * sy;
+      const float qx = nx / sx, qy = ny / sy;
+      const float cross = __fdiv_rn(__fmul_rn(__fmul_rn(rho, nx), ny), sxsy);
+      const float z = __fsub_rn(__fadd_rn(__fmul_rn(qx, qx), __fmul_rn(qy, qy)), __fmul_rn(2.f, cross));
+      const float q = __fsub_rn(1.f, __fmul_rn(rho, rho));
+      float pdf = expf(__fdiv_rn(-z, __fmul_rn(2.f, q)));
+      pdf = __fdiv_rn(pdf, __fmul_rn(6.283185307179586f, __fmul_rn(sxsy, sqrtf(q))));
+      sum += -logf(fmaxf(pdf, 1e-20f));
+      float g0 = 0.f, g1 = 0.f, g2 = 0.f, g3 = 0.f, g4 = 0.f;
+      if (pdf >= 1e-20f) {  // torch.clamp passes the gradient where input >= min
+        const float iq = 1.f / q;
+        g0 = -(qx / sx - rho * qy / sx) * iq;
+        g1 = -(qy / sy - rho * qx / sy) * iq;
+        g2 = 1.f - (qx * qx - cross) * iq;
+        g3 = 1.f - (qy * qy - cross) * iq;
+        g4 = -(nx * ny) / sxsy + z * rho * iq - rho;
+      }
+      dv[i] = g0 * wgt;
+      dv[12 * N + i] = g1 * wgt;
+      dv[24 * N + i] = g2 * wgt;
+      dv[36 * N + i] = g3 * wgt;
+      dv[48 * N + i] = g4 * wgt;
     }
-    dv[i] = g0 * wgt;
-    dv[12 * N + i] = g1 * wgt;
-    dv[24 * N + i] = g2 * wgt;
-    dv[36 * N + i] = g3 * wgt;
-    dv[48 * N + i] = g4 * wgt;
+    sum = warp_sum(sum);
+    if (lane == 0) part[t] = sum;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float tot_s = 0.f;
+#pragma unroll
+      for (int w = 0; w < T_PRED; ++w) tot_s += part[w];
+      loss[s] = tot_s / static_cast<float>(tot);
+    }
+    __syncthreads();
   }
-  sum = warp_sum(sum);
-  if (lane == 0) loss[warp] = sum / static_cast<float>(tot);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -579,11 +616,9 @@ nll_fwd_bwd_kernel(const float* __restrict__ Vpred, const float* __restrict__ Vt
 // 30 threads; ATen's CPU kernel evaluates the update in double, so do we.
 // ---------------------------------------------------------------------------------------
 constexpr int BN_TILE = 128;  // scenes staged per pass (128 x 30 doubles = 30 KB of static shared memory)
-__global__ void __launch_bounds__(256)
-bn_running_update_kernel(const float* __restrict__ stats, const int32_t* __restrict__ seg_off, int S,
-                         double momentum, float* __restrict__ bn, const int32_t* __restrict__ abort_flag) {
-  // a failed peer exchange (peer_exchange.cu) leaves the statistics undefined: leave the buffers alone
-  if (abort_flag && *abort_flag) return;
+__device__ __forceinline__ void bn_running_update_body(const float* __restrict__ stats,
+                                                       const int32_t* __restrict__ seg_off, int S, double momentum,
+                                                       float* __restrict__ bn) {
   // The recurrence is sequential in the scene index, but its inputs are not: 256 threads stage a
   // tile of per-scene statistics (and element counts) in shared memory with coalesced loads, then
   // 30 threads run the recurrence over the tile out of shared memory.
@@ -614,21 +649,43 @@ bn_running_update_kernel(const float* __restrict__ stats, const int32_t* __restr
   if (i < SSTG_N_BN) bn[i] = static_cast<float>(r);
 }
 
+__global__ void __launch_bounds__(256)
+bn_running_update_kernel(const float* __restrict__ stats, const int32_t* __restrict__ seg_off, int S,
+                         double momentum, float* __restrict__ bn, const int32_t* __restrict__ abort_flag) {
+  // a failed peer exchange (peer_exchange.cu) leaves the statistics undefined: leave the buffers alone
+  if (abort_flag && *abort_flag) return;
+  bn_running_update_body(stats, seg_off, S, momentum, bn);
+}
+
 // grad[i] = sum over CTA rows (ascending) of the two partial buffers; parameters that are
 // never executed (tpcnns.4, prelus.4 -- model.py:191) get zero.
+// ascending-row sum of one column; the loads of 8 rows are in flight together, the additions stay in order
+__device__ __forceinline__ float column_sum(const float* __restrict__ p, int rows, int stride) {
+  float s = 0.f;
+  int r = 0;
+  for (; r + 8 <= rows; r += 8) {
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = __ldg(p + static_cast<size_t>(r + j) * stride);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s += v[j];
+  }
+  for (; r < rows; ++r) s += __ldg(p + static_cast<size_t>(r) * stride);
+  return s;
+}
+
+__device__ __forceinline__ float grad_finalize_one(int i, const float* __restrict__ part_st, int rows_st,
+                                                   const float* __restrict__ part_tx, int rows_tx, int tx_stride) {
+  return i < ST_PARAMS ? column_sum(part_st + i, rows_st, ST_PARAMS)
+                       : column_sum(part_tx + (i - ST_PARAMS), rows_tx, tx_stride);
+}
+
 __global__ void grad_finalize_kernel(const float* __restrict__ part_st, int rows_st,
                                      const float* __restrict__ part_tx, int rows_tx, int tx_stride,
                                      float* __restrict__ grad) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= SSTG_N_PARAMS) return;
-  float s = 0.f;
-  if (i < ST_PARAMS) {
-    for (int r = 0; r < rows_st; ++r) s += part_st[static_cast<size_t>(r) * ST_PARAMS + i];
-  } else {
-    const int j = i - ST_PARAMS;
-    for (int r = 0; r < rows_tx; ++r) s += part_tx[static_cast<size_t>(r) * tx_stride + j];
-  }
-  grad[i] = s;
+  grad[i] = grad_finalize_one(i, part_st, rows_st, part_tx, rows_tx, tx_stride);
 }
 
 // SGD (train.py:197: lr only) with optional clip_grad_norm_ (train.py:69-70).
@@ -660,13 +717,40 @@ sgd_step_kernel(float* __restrict__ params, const float* __restrict__ grad, int 
 }
 
 // group loss = sum_s weight[s] * loss[s] (train.py:58-66), fixed order, fp64 accumulate
-__global__ void group_loss_kernel(const float* __restrict__ loss, const float* __restrict__ weight, int S,
-                                  float* __restrict__ out) {
+__device__ __forceinline__ void group_loss_body(const float* __restrict__ loss, const float* __restrict__ weight,
+                                                int S, float* __restrict__ out) {
   double acc = 0.0;
   for (int s = threadIdx.x; s < S; s += 32) acc += static_cast<double>(loss[s]) * (weight ? weight[s] : 1.f);
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
   if (threadIdx.x == 0) *out = static_cast<float>(acc);
+}
+__global__ void group_loss_kernel(const float* __restrict__ loss, const float* __restrict__ weight, int S,
+                                  float* __restrict__ out) {
+  group_loss_body(loss, weight, S, out);
+}
+
+// The tail of one optimiser group in ONE launch (the group is latency-bound: four dependent launches of
+// ~3-16 us each become one): CTAs 0..n-3 reduce the gradient partial rows and, when no clipping is asked
+// for, apply SGD on the spot; CTA n-2 runs the BatchNorm recurrence; CTA n-1 the group loss.
+constexpr int TAIL_FIN_CTAS = (SSTG_N_PARAMS + 255) / 256;
+__global__ void __launch_bounds__(256)
+train_tail_kernel(const float* __restrict__ part_st, int rows_st, const float* __restrict__ part_tx, int rows_tx,
+                  int tx_stride, float* __restrict__ grad, float* __restrict__ params, float lr,
+                  const float* __restrict__ stats, const int32_t* __restrict__ seg_off, int S, double momentum,
+                  float* __restrict__ bn, const float* __restrict__ loss, const float* __restrict__ weight,
+                  float* __restrict__ group_loss) {
+  if (blockIdx.x < TAIL_FIN_CTAS) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= SSTG_N_PARAMS) return;
+    const float g = grad_finalize_one(i, part_st, rows_st, part_tx, rows_tx, tx_stride);
+    grad[i] = g;
+    if (lr != 0.f) params[i] = fmaf(-lr, g, params[i]);
+  } else if (blockIdx.x == TAIL_FIN_CTAS) {
+    if (momentum >= 0.0) bn_running_update_body(stats, seg_off, S, momentum, bn);
+  } else if (group_loss != nullptr && threadIdx.x < 32) {
+    group_loss_body(loss, weight, S, group_loss);
+  }
 }
 
 size_t train_fwd_smem(int NP) {
@@ -732,7 +816,8 @@ int launch_stgcn_train_backward(const float* V, const float* A, const int32_t* s
 int launch_nll_fwd_bwd(const float* Vpred, const float* Vtr, const int32_t* seg_off, int S, const float* weight,
                        float* loss, float* dV, cudaStream_t st) {
   if (S == 0) return SSTG_OK;
-  nll_fwd_bwd_kernel<<<(S + 7) / 8, 256, 0, st>>>(Vpred, Vtr, seg_off, S, weight, loss, dV);
+  const int cap = 8 * 148;
+  nll_fwd_bwd_kernel<<<S < cap ? S : cap, NLL_THREADS, 0, st>>>(Vpred, Vtr, seg_off, S, weight, loss, dV);
   SSTG_CUDA_TRY(cudaGetLastError(), "nll_fwd_bwd launch");
   return SSTG_OK;
 }
@@ -750,6 +835,16 @@ int launch_grad_finalize(const float* part_st, int rows_st, const float* part_tx
   grad_finalize_kernel<<<(SSTG_N_PARAMS + 255) / 256, 256, 0, st>>>(part_st, rows_st, part_tx, rows_tx, tx_stride,
                                                                    grad);
   SSTG_CUDA_TRY(cudaGetLastError(), "grad_finalize launch");
+  return SSTG_OK;
+}
+
+int launch_train_tail(const float* part_st, int rows_st, const float* part_tx, int rows_tx, int tx_stride,
+                      float* grad, float* params, float lr, const float* stats, const int32_t* seg_off, int S,
+                      double momentum, float* bn, const float* loss, const float* weight, float* group_loss,
+                      cudaStream_t st) {
+  train_tail_kernel<<<TAIL_FIN_CTAS + 2, 256, 0, st>>>(part_st, rows_st, part_tx, rows_tx, tx_stride, grad, params, lr,
+                                                      stats, seg_off, S, momentum, bn, loss, weight, group_loss);
+  SSTG_CUDA_TRY(cudaGetLastError(), "train_tail launch");
   return SSTG_OK;
 }
 

@@ -16,6 +16,13 @@
 // per unit, and the totals go to a per-CTA shared accumulator that only that warp touches
 // -- so the order of every floating-point addition is fixed (no atomics).  Each CTA writes
 // its accumulator as one row of `partial`; sstg_grad_finalize adds the rows in order.
+//
+// Small tiles (the reference's optimiser groups are ~128 scenes of ~10 pedestrians: one scene per CTA,
+// the step is LATENCY-bound): a tile of <= 64 columns spreads each column's transposed convolution over
+// 2 or 4 lanes (slices of the 12 channels, butterfly-summed so all lanes hold the same bits), gives every
+// (output channel, input channel) weight-gradient unit to ONE thread (9 taps in registers, columns in
+// ascending order, no reduction at all), and every global load phase issues all its loads before the
+// first use.
 #include "txpcnn_common.cuh"
 
 namespace sstg {
@@ -27,6 +34,18 @@ using namespace txp;
 constexpr int B_WT = 5 * X_WL;                     // transposed weights, 12 "input" channels per layer
 constexpr int B_GRAD = SSTG_N_PARAMS - P_TP0_W;    // 7421 TXP-CNN parameters
 constexpr int B_GRAD_STRIDE = SSTG_TXP_GRAD_STRIDE;
+
+// -DSSTG_PHASE_CLOCKS: thread 0 of every CTA stamps clock64() at the phase boundaries of its FIRST tile
+// (profiling aid for the latency-bound small-group case; read back with sstg_debug_phase_clocks).
+#ifdef SSTG_PHASE_CLOCKS
+__device__ long long g_phase[160 * 40];
+#define PHASE(k)                                                                         \
+  do {                                                                                   \
+    if (threadIdx.x == 0 && tile == static_cast<int>(blockIdx.x)) g_phase[blockIdx.x * 40 + (k)] = clock64(); \
+  } while (0)
+#else
+#define PHASE(k)
+#endif
 
 struct BSmem {
   float wT[B_WT];
@@ -121,6 +140,50 @@ __device__ __forceinline__ void dw_unit(const float* __restrict__ DU, const floa
   }
 }
 
+// Small tile: thread `unit` owns dW[co][ci][0..8]; it walks the tile's columns in ascending order with a
+// sliding 5x3 window of x, so the sum order is fixed and no cross-lane reduction is needed.
+__device__ __forceinline__ void dw_unit_thread(const float* __restrict__ DU, const float* __restrict__ XT, int Wp,
+                                               int c_end, int co, int ci, int cin, float* __restrict__ gw) {
+  float acc[9];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) acc[k] = 0.f;
+  const float* xr = XT + (ci * 5) * Wp;
+  const float* dr = DU + (co * 5) * Wp;
+  float x0[5], x1[5], x2[5];
+#pragma unroll
+  for (int h = 0; h < 5; ++h) {
+    x0[h] = xr[h * Wp];      // column 0 is a zero separator
+    x1[h] = xr[h * Wp + 1];
+  }
+  for (int c = 1; c <= c_end; ++c) {
+    float d[5];
+#pragma unroll
+    for (int h = 0; h < 5; ++h) {
+      x2[h] = xr[h * Wp + c + 1];
+      d[h] = dr[h * Wp + c];
+    }
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+      for (int h = 0; h < 5; ++h) {
+        const int hi = h + kh - 1;
+        if (hi >= 0 && hi < 5) {
+          acc[kh * 3 + 0] = fmaf(d[h], x0[hi], acc[kh * 3 + 0]);
+          acc[kh * 3 + 1] = fmaf(d[h], x1[hi], acc[kh * 3 + 1]);
+          acc[kh * 3 + 2] = fmaf(d[h], x2[hi], acc[kh * 3 + 2]);
+        }
+      }
+#pragma unroll
+    for (int h = 0; h < 5; ++h) {
+      x0[h] = x1[h];
+      x1[h] = x2[h];
+    }
+  }
+  float* g = gw + (co * cin + ci) * 9;
+#pragma unroll
+  for (int k = 0; k < 9; ++k) g[k] += acc[k];
+}
+
 template <int JX>
 __global__ void __launch_bounds__(X_THREADS, 1)
 txpcnn_bwd_kernel(const float* __restrict__ dOut, const float* __restrict__ Usave, const float* __restrict__ Xsave,
@@ -134,32 +197,53 @@ txpcnn_bwd_kernel(const float* __restrict__ dOut, const float* __restrict__ Usav
   float* gacc = XT + X_ROWS * Wp;                                                        // [B_GRAD_STRIDE]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int half = tid / X_COLS;
-  const int qt = tid - half * X_COLS;
+  const int idx = tid - half * X_COLS;
 
   // ---- transposed + flipped weights, tap-major for the packed column convolution:
   //      wT[l][(b*2 + hf)*56 + tap'*6 + a6] = W_l[b][hf*6 + a6][8 - tap']
-  for (int i = tid; i < B_WT; i += X_THREADS) {
-    const int l = i / X_WL, r = i % X_WL;
-    const int b = r / (2 * X_WSLOT), r2 = r % (2 * X_WSLOT);
-    const int hf = r2 / X_WSLOT, r3 = r2 % X_WSLOT;
-    float v = 0.f;
-    if (r3 < 54) {
-      const int a = hf * 6 + r3 % 6, tap = r3 / 6;
-      const int cin = (l == 0) ? 8 : 12;
-      if (a < cin) v = params[w_base(l) + (b * cin + a) * 9 + (8 - tap)];
+  //      (loads issued in batches of W_BATCH before the first store: one L2 round trip per batch)
+  constexpr int W_BATCH = 9;
+  for (int i0 = tid; i0 < B_WT; i0 += W_BATCH * X_THREADS) {
+    float v[W_BATCH];
+#pragma unroll
+    for (int j = 0; j < W_BATCH; ++j) {
+      const int i = i0 + j * X_THREADS;
+      v[j] = 0.f;
+      if (i < B_WT) {
+        const int l = i / X_WL, r = i % X_WL;
+        const int b = r / (2 * X_WSLOT), r2 = r % (2 * X_WSLOT);
+        const int hf = r2 / X_WSLOT, r3 = r2 % X_WSLOT;
+        if (r3 < 54) {
+          const int a = hf * 6 + r3 % 6, tap = r3 / 6;
+          const int cin = (l == 0) ? 8 : 12;
+          if (a < cin) v[j] = params[w_base(l) + (b * cin + a) * 9 + (8 - tap)];
+        }
+      }
     }
-    sm.wT[i] = v;
+#pragma unroll
+    for (int j = 0; j < W_BATCH; ++j) {
+      const int i = i0 + j * X_THREADS;
+      if (i < B_WT) sm.wT[i] = v[j];
+    }
   }
   if (tid < 4) sm.slope[tid] = params[P_PRELUS + tid];
   for (int i = tid; i < B_GRAD_STRIDE; i += X_THREADS) gacc[i] = 0.f;
   float dsl[4] = {0.f, 0.f, 0.f, 0.f};
 
+#ifdef SSTG_PHASE_CLOCKS
+  if (threadIdx.x == 0) g_phase[blockIdx.x * 40 + 39] = clock64();
+#endif
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    PHASE(0);
     const int s_lo = tile_off[tile], s_hi = tile_off[tile + 1];
     const int p_lo = seg_off[s_lo];
     const int cols = seg_off[s_hi] - p_lo;
     const int nsc = s_hi - s_lo;
     const int c_end = cols + nsc - 1;  // last data column of the shared tile
+    // lanes per column of the transposed convolution (CTA-uniform): 4 / 2 for small tiles, else 1
+    const int cgs = cols <= X_COLS / 4 ? 4 : (cols <= X_COLS / 2 ? 2 : 1);
+    const int qt = cgs == 4 ? (idx >> 2) : (cgs == 2 ? (idx >> 1) : idx);
+    const int cg = idx & (cgs - 1);
     __syncthreads();
     for (int q = tid; q < cols; q += X_THREADS) {
       int j = 0;
@@ -176,6 +260,7 @@ txpcnn_bwd_kernel(const float* __restrict__ dOut, const float* __restrict__ Usav
       XT[row * Wp + col] = 0.f;
     }
     __syncthreads();
+    PHASE(1);
 
     int sc[JX], gN[JX];
     long long gO[JX];
@@ -195,28 +280,54 @@ txpcnn_bwd_kernel(const float* __restrict__ dOut, const float* __restrict__ Usav
 #pragma unroll
         for (int h = 0; h < 5; ++h) {
           const int row = (half * 6 + co) * 5 + h;
-          const float g = on[u] ? dOut[gO[u] + static_cast<long long>(row) * gN[u]] : 0.f;
+          const float g = on[u] ? __ldg(dOut + gO[u] + static_cast<long long>(row) * gN[u]) : 0.f;
           (co & 1 ? G[u][co >> 1][h].y : G[u][co >> 1][h].x) = g;
-          if (on[u]) DU[row * Wp + sc[u]] = g;
         }
-    }
-    // x4 -> XT
-    {
-      const float* xb = Xsave + 3 * layer_stride + static_cast<long long>(p_lo) * 60;
-      for (int i = tid; i < X_ROWS * cols; i += X_THREADS) {
-        const int row = i / cols, q = i - row * cols;
-        const int sb = sm.sbase[q];
-        XT[row * Wp + sm.scol[q]] = xb[sb * 60 + (q - sb) + row * sm.nstr[q]];
+      if (on[u]) {
+#pragma unroll
+        for (int co = 0; co < 6; ++co)
+#pragma unroll
+          for (int h = 0; h < 5; ++h)
+            DU[((half * 6 + co) * 5 + h) * Wp + sc[u]] = (co & 1) ? G[u][co >> 1][h].y : G[u][co >> 1][h].x;
       }
     }
+    // activation planes -> XT: `rows` rows of a [rows][N] block per scene; 4 loads in flight per thread
+    auto fill_xt = [&](const float* __restrict__ xb, int rows) {
+      const int n = rows * cols;
+      for (int i0 = tid; i0 < n; i0 += 4 * X_THREADS) {
+        float v[4];
+        int dst[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int i = i0 + j * X_THREADS;
+          dst[j] = -1;
+          if (i < n) {
+            const int row = i / cols, q = i - row * cols;
+            const int sb = sm.sbase[q];
+            dst[j] = row * Wp + sm.scol[q];
+            v[j] = __ldg(xb + sb * rows + (q - sb) + row * sm.nstr[q]);
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (dst[j] >= 0) XT[dst[j]] = v[j];
+      }
+    };
+    fill_xt(Xsave + 3 * layer_stride + static_cast<long long>(p_lo) * 60, 60);  // x4
     __syncthreads();
+    PHASE(2);
 
 #pragma unroll 1
     for (int l = 4; l >= 0; --l) {
       const int cin = (l == 0) ? 8 : 12;
+      PHASE(3 + (4 - l) * 6);
       // ---- weight and bias gradients of layer l
       float* gw = gacc + (w_base(l) - P_TP0_W);
-      for (int unit = warp; unit < 2 * cin; unit += 8) dw_unit(DU, XT, Wp, c_end, unit >> 1, unit & 1, cin, lane, gw);
+      if (cgs > 1) {
+        if (tid < 12 * cin) dw_unit_thread(DU, XT, Wp, c_end, tid / cin, tid % cin, cin, gw);
+      } else {
+        for (int unit = warp; unit < 2 * cin; unit += 8) dw_unit(DU, XT, Wp, c_end, unit >> 1, unit & 1, cin, lane, gw);
+      }
       for (int co = warp; co < 12; co += 8) {
         float sb_ = 0.f;
         for (int c = 1 + lane; c <= c_end; c += 32)
@@ -225,6 +336,7 @@ txpcnn_bwd_kernel(const float* __restrict__ dOut, const float* __restrict__ Usav
         sb_ = warp_sum(sb_);
         if (lane == 0) gacc[b_base(l) - P_TP0_W + co] += sb_;
       }
+      PHASE(4 + (4 - l) * 6);
       // ---- transposed convolution: T = conv_l^T(du_l)
       float2 T[JX][3][5];
 #pragma unroll
@@ -233,13 +345,35 @@ txpcnn_bwd_kernel(const float* __restrict__ dOut, const float* __restrict__ Usav
         for (int pr = 0; pr < 3; ++pr)
 #pragma unroll
           for (int h = 0; h < 5; ++h) T[u][pr][h] = make_float2(0.f, 0.f);
-        if (on[u]) conv_column2<12>(DU, Wp, sc[u], sm.wT + l * X_WL, half, T[u]);
+        if (cgs == 1) {
+          if (on[u]) conv_column2<12>(DU, Wp, sc[u], sm.wT + l * X_WL, half, T[u]);
+        } else {
+          // a slice of the 12 channels per lane, then a butterfly over the 2 / 4 lanes of the column:
+          // fp32 addition commutes, so every lane ends with the same bits
+          if (on[u]) {
+            if (cgs == 4) conv_column2<3>(DU, Wp, sc[u], sm.wT + l * X_WL, half, T[u], cg * 3);
+            else conv_column2<6>(DU, Wp, sc[u], sm.wT + l * X_WL, half, T[u], cg * 6);
+          }
+#pragma unroll
+          for (int pr = 0; pr < 3; ++pr)
+#pragma unroll
+            for (int h = 0; h < 5; ++h) {
+              T[u][pr][h].x += __shfl_xor_sync(0xffffffffu, T[u][pr][h].x, 1);
+              T[u][pr][h].y += __shfl_xor_sync(0xffffffffu, T[u][pr][h].y, 1);
+              if (cgs == 4) {
+                T[u][pr][h].x += __shfl_xor_sync(0xffffffffu, T[u][pr][h].x, 2);
+                T[u][pr][h].y += __shfl_xor_sync(0xffffffffu, T[u][pr][h].y, 2);
+              }
+            }
+        }
       }
+      PHASE(5 + (4 - l) * 6);
       __syncthreads();  // every read of DU / XT for layer l is done
+      PHASE(6 + (4 - l) * 6);
       if (l == 0) {
 #pragma unroll
         for (int u = 0; u < JX; ++u)
-          if (on[u]) {
+          if (on[u] && cg == 0) {
             const int q = qt + u * X_COLS;
             const int sb = sm.sbase[q];
             float* o = dH + static_cast<long long>(p_lo + sb) * 40 + (q - sb);
@@ -255,8 +389,17 @@ txpcnn_bwd_kernel(const float* __restrict__ dOut, const float* __restrict__ Usav
       }
       const int k = l - 1;  // next layer down: x_{k+1} = PReLU_k(u_k) (+ x_k for k >= 1)
       const float slope = sm.slope[k];
+      const float cnt = cg == 0 ? 1.f : 0.f;  // the lanes sharing a column hold the same values: one of them counts
 #pragma unroll
-      for (int u = 0; u < JX; ++u)
+      for (int u = 0; u < JX; ++u) {
+        float uv[6][5];  // all 30 loads are issued before the first use
+#pragma unroll
+        for (int co = 0; co < 6; ++co)
+#pragma unroll
+          for (int h = 0; h < 5; ++h)
+            uv[co][h] = on[u] ? __ldg(Usave + k * layer_stride + gO[u] +
+                                      static_cast<long long>((half * 6 + co) * 5 + h) * gN[u])
+                              : 1.f;
 #pragma unroll
         for (int co = 0; co < 6; ++co)
 #pragma unroll
@@ -267,30 +410,24 @@ txpcnn_bwd_kernel(const float* __restrict__ dOut, const float* __restrict__ Usav
             Gr = g;
             if (on[u]) {
               const int row = (half * 6 + co) * 5 + h;
-              const float uv = Usave[k * layer_stride + gO[u] + static_cast<long long>(row) * gN[u]];
-              const bool pos = uv > 0.f;
-              if (!pos) dsl[k] = fmaf(g, uv, dsl[k]);
+              const bool pos = uv[co][h] > 0.f;
+              if (!pos) dsl[k] = fmaf(g * cnt, uv[co][h], dsl[k]);
               DU[row * Wp + sc[u]] = pos ? g : slope * g;
             }
           }
-      if (k >= 1) {
-        const float* xb = Xsave + (k - 1) * layer_stride + static_cast<long long>(p_lo) * 60;
-        for (int i = tid; i < X_ROWS * cols; i += X_THREADS) {
-          const int row = i / cols, q = i - row * cols;
-          const int sb = sm.sbase[q];
-          XT[row * Wp + sm.scol[q]] = xb[sb * 60 + (q - sb) + row * sm.nstr[q]];
-        }
-      } else {
-        const float* xb = Hin + static_cast<long long>(p_lo) * 40;
-        for (int i = tid; i < 40 * cols; i += X_THREADS) {
-          const int row = i / cols, q = i - row * cols;
-          const int sb = sm.sbase[q];
-          XT[row * Wp + sm.scol[q]] = xb[sb * 40 + (q - sb) + row * sm.nstr[q]];
-        }
       }
+      PHASE(7 + (4 - l) * 6);
+      if (k >= 1)
+        fill_xt(Xsave + (k - 1) * layer_stride + static_cast<long long>(p_lo) * 60, 60);
+      else
+        fill_xt(Hin + static_cast<long long>(p_lo) * 40, 40);
+      PHASE(8 + (4 - l) * 6);
       __syncthreads();
     }
   }
+#ifdef SSTG_PHASE_CLOCKS
+  if (threadIdx.x == 0) g_phase[blockIdx.x * 40 + 38] = clock64();
+#endif
 
   // ---- PReLU slope gradients: CTA reduction in warp order, then the partial row
   __syncthreads();
@@ -311,6 +448,12 @@ txpcnn_bwd_kernel(const float* __restrict__ dOut, const float* __restrict__ Usav
 }
 
 }  // namespace
+
+#ifdef SSTG_PHASE_CLOCKS
+extern "C" int sstg_debug_phase_clocks(long long* host_out, int n) {
+  return cudaMemcpyFromSymbol(host_out, g_phase, sizeof(long long) * (n < 160 * 40 ? n : 160 * 40)) == cudaSuccess ? 0 : -3;
+}
+#endif
 
 int txpcnn_bwd_rows(int n_tiles) {
   int dev = 0, sms = 148;

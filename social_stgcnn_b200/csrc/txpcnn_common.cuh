@@ -33,11 +33,13 @@ __device__ __forceinline__ void ffma2(float2& d, const float2 a, const float2 b)
 // One 3x3 layer for one column with packed FMAs: acc[pr][h] holds output channels
 // (half*6 + 2 pr, half*6 + 2 pr + 1) at feature row h.  Weight slot layout (forward only):
 // wl[(ci*2 + half)*56 + tap*6 + co6] -- tap-major, so an LDS.128 delivers aligned channel pairs.
+// CI input channels starting at ci0 (ci0 > 0: a partial sum over a slice of the input channels).
 template <int CI>
 __device__ __forceinline__ void conv_column2(const float* __restrict__ act, int Wp, int sc,
-                                             const float* __restrict__ wl, int half, float2 (&acc)[3][5]) {
+                                             const float* __restrict__ wl, int half, float2 (&acc)[3][5],
+                                             int ci0 = 0) {
 #pragma unroll 2
-  for (int ci = 0; ci < CI; ++ci) {
+  for (int ci = ci0; ci < ci0 + CI; ++ci) {
     float2 x[5][3];
     const float* a = act + (ci * 5) * Wp + sc - 1;
 #pragma unroll
