@@ -95,6 +95,14 @@ __device__ __forceinline__ void bulk_wait_read() {
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// ---- programmatic dependent launch (the training step is a chain of short kernels: each one's prologue --
+// weight staging out of `params`, table set-up -- runs underneath its predecessor's main body).
+// Rules kept by every kernel that uses them: nothing produced by an earlier kernel is read before pdl_wait();
+// dependents are released only AFTER this kernel's own wait (so a prologue never overlaps the kernel two
+// places back); kernels that WRITE `params` or the plan tables never release early.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_release() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 __device__ __forceinline__ float prelu(float x, float a) { return x >= 0.f ? x : a * x; }
 __device__ __forceinline__ float rsqrt_fast(float x) {
   float y;
@@ -106,6 +114,25 @@ __device__ __forceinline__ float rsqrt_fast(float x) {
 __device__ __forceinline__ float inv_dist(float sq) { return sq >= 1.17549435e-38f ? rsqrt_fast(sq) : 0.f; }
 
 #endif  // __CUDACC__
+
+#ifdef __CUDACC__
+// <<<grid, block, smem, st>>> with programmatic stream serialization allowed (the kernel must call pdl_wait()).
+template <class... KArgs, class... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                              Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+#endif
 
 // launchers (one per .cu file)
 int launch_graph_build(const float* rel, const int32_t* seg_off, const int64_t* a_off, int S, int T, int max_n,

@@ -23,6 +23,18 @@ namespace sstg {
 
 namespace {
 
+// -DSSTG_PHASE_CLOCKS: thread 0 of every CTA stamps clock64() at the phase boundaries of its first scene
+// (profiling aid for the latency-bound small-group case; read back with sstg_debug_phase_clocks_st).
+#ifdef SSTG_PHASE_CLOCKS
+__device__ long long g_phase_st[300 * 24];
+#define PHASE_ST(k)                                                                                      \
+  do {                                                                                                   \
+    if (threadIdx.x == 0 && s == static_cast<int>(blockIdx.x)) g_phase_st[blockIdx.x * 24 + (k)] = clock64(); \
+  } while (0)
+#else
+#define PHASE_ST(k)
+#endif
+
 constexpr int R_WARPS = T_OBS;
 constexpr int R_THREADS = R_WARPS * 32;
 constexpr int ST_PARAMS = P_TP0_W;  // 142 st_gcn parameters come first in the flat block
@@ -106,11 +118,17 @@ stgcn_train_fwd_kernel(const float* __restrict__ V, const float* __restrict__ A,
   float* gbuf = red + R_WARPS * 10;                                                             // [8][NP][8]
   float* pbuf = gbuf + R_WARPS * NP * 8;                                                        // [5][8][NP]
   const int tid = threadIdx.x, lane = tid & 31, t = tid >> 5;
+#ifdef SSTG_PHASE_CLOCKS
+  if (tid == 0) g_phase_st[blockIdx.x * 24 + 12] = clock64();
+#endif
   load_train_params(tp, params);
+  pdl_wait();
+  pdl_release();
   __syncthreads();
   float* gw = gbuf + static_cast<size_t>(t) * NP * 8;
 
   for (int s = blockIdx.x; s < S; s += gridDim.x) {
+    PHASE_ST(13);
     const int n0 = seg_off[s], N = seg_off[s + 1] - n0;
     const float invM = 1.f / static_cast<float>(T_OBS * N);
     const float2* vp = reinterpret_cast<const float2*>(V) + (static_cast<size_t>(n0) * T_OBS + static_cast<size_t>(t) * N);
@@ -150,6 +168,7 @@ stgcn_train_fwd_kernel(const float* __restrict__ V, const float* __restrict__ A,
         y[4][j] = fmaf(g5, a, y[4][j]);
       }
     }
+    PHASE_ST(14);
     // residual branch pre-BN: r = Wr v + br
     float r[C][NJ];
 #pragma unroll
@@ -197,6 +216,7 @@ stgcn_train_fwd_kernel(const float* __restrict__ V, const float* __restrict__ A,
       st[20 + tid] = m[5 + tid];
       st[25 + tid] = q[5 + tid];
     }
+    PHASE_ST(15);
     // ---- BN1 + PReLU1 -> shared p; save y
     float* Ys = Y + static_cast<size_t>(n0) * 40;
 #pragma unroll
@@ -213,6 +233,7 @@ stgcn_train_fwd_kernel(const float* __restrict__ V, const float* __restrict__ A,
       }
     }
     __syncthreads();
+    PHASE_ST(16);
     // ---- (3,1) temporal conv
     float z[C][NJ];
 #pragma unroll
@@ -235,6 +256,7 @@ stgcn_train_fwd_kernel(const float* __restrict__ V, const float* __restrict__ A,
         }
       }
     }
+    PHASE_ST(17);
     float mz[5], qz[5];
 #pragma unroll
     for (int c = 0; c < C; ++c) {
@@ -266,6 +288,7 @@ stgcn_train_fwd_kernel(const float* __restrict__ V, const float* __restrict__ A,
       st[10 + tid] = mz[tid];
       st[15 + tid] = qz[tid];
     }
+    PHASE_ST(18);
     float* Zs = Z + static_cast<size_t>(n0) * 40;
     float* Hs = H + static_cast<size_t>(n0) * 40;
 #pragma unroll
@@ -283,6 +306,7 @@ stgcn_train_fwd_kernel(const float* __restrict__ V, const float* __restrict__ A,
         }
       }
     }
+    PHASE_ST(19);
   }
 }
 
@@ -297,14 +321,19 @@ stgcn_train_bwd_kernel(const float* __restrict__ V, const float* __restrict__ A,
                        const float* __restrict__ dH, float* __restrict__ partial) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   TrainParams& tp = *reinterpret_cast<TrainParams*>(smem_raw);
-  float* red = reinterpret_cast<float*>(smem_raw + ((sizeof(TrainParams) + 15) & ~size_t(15)));  // [8][100]
-  float* gsum = red + R_WARPS * 100;                     // [144] per-CTA sums of the per-scene-reduced grads
+  float* red = reinterpret_cast<float*>(smem_raw + ((sizeof(TrainParams) + 15) & ~size_t(15)));  // [8][128]
+  float* gsum = red + R_WARPS * 128;                     // [144] per-CTA sums of the per-scene-reduced grads
   float* pb = gsum + 144;                                // [5][8][NP]  p = PReLU1(BN1(y))
   float* dz = pb + C * T_OBS * NP;                       // [5][8][NP]  dL/dz
   float* dq = dz + C * T_OBS * NP;                       // [5][8][NP]  dL/dq, then dL/dy in place
   const int tid = threadIdx.x, lane = tid & 31, t = tid >> 5;
+#ifdef SSTG_PHASE_CLOCKS
+  if (tid == 0) g_phase_st[blockIdx.x * 24 + 0] = clock64();
+#endif
   load_train_params(tp, params);
   if (tid < 144) gsum[tid] = 0.f;
+  pdl_wait();
+  pdl_release();
   __syncthreads();
 
   // per-thread gradient partials carried over all scenes of this CTA
@@ -318,6 +347,7 @@ stgcn_train_bwd_kernel(const float* __restrict__ V, const float* __restrict__ A,
   }
 
   for (int s = blockIdx.x; s < S; s += gridDim.x) {
+    PHASE_ST(1);
     const int n0 = seg_off[s], N = seg_off[s + 1] - n0;
     const float M = static_cast<float>(T_OBS * N), invM = 1.f / M;
     const float* st = stats + static_cast<size_t>(s) * SSTG_N_BN;
@@ -356,7 +386,9 @@ stgcn_train_bwd_kernel(const float* __restrict__ V, const float* __restrict__ A,
         sA[10 + c] = fmaf(ds, xhr, sA[10 + c]);
       }
     }
+    PHASE_ST(2);
     block_sum<15>(sA, red);
+    PHASE_ST(3);
     if (tid < 15) gsum[tid] += sA[tid];  // [0..4] dbeta2 (= dbeta_r), [5..9] dgamma2, [10..14] dgamma_r
 
     // ---- phase B: d_z, d_r; p = PReLU1(BN1(y)) to shared
@@ -382,6 +414,7 @@ stgcn_train_bwd_kernel(const float* __restrict__ V, const float* __restrict__ A,
       }
     }
     __syncthreads();
+    PHASE_ST(4);
 
     // ---- phase C: temporal-conv backward (weights, bias, input), PReLU1 backward, BN1 sums
     float sC[10];
@@ -430,7 +463,9 @@ stgcn_train_bwd_kernel(const float* __restrict__ V, const float* __restrict__ A,
         sC[5 + c] = fmaf(dqc, xh1, sC[5 + c]);
       }
     }
+    PHASE_ST(5);
     block_sum<10>(sC, red);
+    PHASE_ST(6);
     if (tid < 10) gsum[16 + tid] += sC[tid];  // [16..20] dbeta1, [21..25] dgamma1
 
     // ---- phase D: BN1 backward -> d_y (in place in dq; only this warp touches row t)
@@ -444,8 +479,9 @@ stgcn_train_bwd_kernel(const float* __restrict__ V, const float* __restrict__ A,
       }
     }
     __syncwarp();
+    PHASE_ST(7);
     // ---- phase E: d_g[c, t, v] = sum_w d_y[c, t, w] A[t, v, w];  dWg, dbg.
-    // Lanes <-> source nodes v, each lane walks ITS row of A (w ascending, 4 loads in flight) against
+    // Lanes <-> source nodes v, each lane walks ITS row of A (w ascending, 8 loads in flight) against
     // d_y broadcast from shared memory: no cross-lane reduction and no load->shuffle chain per node --
     // the per-node latency chain was what set the duration of a small group.  A[t] is at most 16 KB per
     // warp at N = 64 and stays in L1 across the strided row walk.
@@ -455,12 +491,12 @@ stgcn_train_bwd_kernel(const float* __restrict__ V, const float* __restrict__ A,
       const float* row = At + static_cast<size_t>(v) * N;
       float pg[C] = {0.f, 0.f, 0.f, 0.f, 0.f};
       int w = 0;
-      for (; w + 4 <= N; w += 4) {
-        float a[4];
+      for (; w + 8 <= N; w += 8) {
+        float a[8];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) a[j] = __ldg(row + w + j);
+        for (int j = 0; j < 8; ++j) a[j] = __ldg(row + w + j);
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
+        for (int j = 0; j < 8; ++j)
 #pragma unroll
           for (int c = 0; c < C; ++c) pg[c] = fmaf(dyt[c * T_OBS * NP + w + j], a[j], pg[c]);
       }
@@ -477,12 +513,21 @@ stgcn_train_bwd_kernel(const float* __restrict__ V, const float* __restrict__ A,
         dbg[c] += pg[c];
       }
     }
+    PHASE_ST(8);
     __syncthreads();  // pb / dz / dq are rewritten by the next scene
+    PHASE_ST(9);
   }
+#ifdef SSTG_PHASE_CLOCKS
+  if (tid == 0) g_phase_st[blockIdx.x * 24 + 10] = clock64();
+#endif
 
-  // ---- CTA reduction of the carried partials, fixed order, then the partial row
+  // ---- CTA reduction of the carried partials, fixed order, then the partial row.
+  // 112 per-thread values (97 carried + dWg/dbg), padded to 128: a warp reduce-scatter (at each butterfly
+  // step a lane hands over the half its partner keeps: 64+32+16+8+4 shuffles instead of 112 x 5) leaves lane
+  // L with the warp totals of values 4L..4L+3; thread i < 112 then adds the 8 warps in ascending order and
+  // stores parameter i of the row -- no serial tail on one thread.
   {
-    float v1[97];
+    float v1[128];
     int i = 0;
 #pragma unroll
     for (int c = 0; c < C; ++c) {
@@ -501,45 +546,54 @@ stgcn_train_bwd_kernel(const float* __restrict__ V, const float* __restrict__ A,
     for (int c = 0; c < C; ++c) v1[i++] = db2[c];
     v1[i++] = da1;
     v1[i++] = da2;
-    block_sum<97>(v1, red);
-    // dWg/dbg: lanes, then warps in ascending order through shared
 #pragma unroll
     for (int c = 0; c < C; ++c) {
-      dWg[c][0] = warp_sum(dWg[c][0]);
-      dWg[c][1] = warp_sum(dWg[c][1]);
-      dbg[c] = warp_sum(dbg[c]);
+      v1[i++] = dWg[c][0];
+      v1[i++] = dWg[c][1];
     }
-    if (lane == 0) {
 #pragma unroll
-      for (int c = 0; c < C; ++c) {
-        red[t * 16 + 2 * c] = dWg[c][0];
-        red[t * 16 + 2 * c + 1] = dWg[c][1];
-        red[t * 16 + 10 + c] = dbg[c];
+    for (int c = 0; c < C; ++c) v1[i++] = dbg[c];
+#pragma unroll
+    for (int j = 112; j < 128; ++j) v1[j] = 0.f;
+#pragma unroll
+    for (int half = 64; half >= 4; half >>= 1) {
+      const int o = half >> 2;                       // lane offsets 16, 8, 4, 2, 1
+      const bool up = (lane & o) != 0;               // this lane keeps the upper half
+#pragma unroll
+      for (int j = 0; j < half; ++j) {
+        const float send = up ? v1[j] : v1[j + half];
+        const float keep = up ? v1[j + half] : v1[j];
+        v1[j] = keep + __shfl_xor_sync(0xffffffffu, send, o);
       }
     }
+    *reinterpret_cast<float4*>(red + t * 128 + 4 * lane) = make_float4(v1[0], v1[1], v1[2], v1[3]);
     __syncthreads();
     float* out = partial + static_cast<size_t>(blockIdx.x) * ST_PARAMS;
-    if (tid == 0) {
-      for (int j = 0; j < 15; ++j) {
-        float sum = 0.f;
-        for (int w = 0; w < R_WARPS; ++w) sum += red[w * 16 + j];
-        out[(j < 10) ? (P_GCN_W + j) : (P_GCN_B + j - 10)] = sum;
-      }
-      for (int j = 0; j < 10; ++j) out[P_RES_W + j] = v1[j];
-      for (int j = 0; j < 5; ++j) out[P_RES_B + j] = v1[10 + j];
-      for (int j = 0; j < 75; ++j) out[P_TCN_W + j] = v1[15 + j];
-      for (int j = 0; j < 5; ++j) out[P_TCN_B + j] = v1[90 + j];
-      out[P_PRELU1] = v1[95];
-      out[P_PRELU2] = v1[96];
-      for (int c = 0; c < C; ++c) {
-        out[P_BN2_B + c] = gsum[c];
-        out[P_BNR_B + c] = gsum[c];
-        out[P_BN2_G + c] = gsum[5 + c];
-        out[P_BNR_G + c] = gsum[10 + c];
-        out[P_BN1_B + c] = gsum[16 + c];
-        out[P_BN1_G + c] = gsum[21 + c];
-      }
+    if (tid < 112) {
+      float sum = 0.f;
+#pragma unroll
+      for (int w = 0; w < R_WARPS; ++w) sum += red[w * 128 + tid];
+      const int dst = tid < 10 ? P_RES_W + tid
+                    : tid < 15 ? P_RES_B + tid - 10
+                    : tid < 90 ? P_TCN_W + tid - 15
+                    : tid < 95 ? P_TCN_B + tid - 90
+                    : tid == 95 ? P_PRELU1
+                    : tid == 96 ? P_PRELU2
+                    : tid < 107 ? P_GCN_W + tid - 97
+                                : P_GCN_B + tid - 107;
+      out[dst] = sum;
+    } else if (tid >= 128 && tid < 128 + C) {
+      const int c = tid - 128;
+      out[P_BN2_B + c] = gsum[c];
+      out[P_BNR_B + c] = gsum[c];
+      out[P_BN2_G + c] = gsum[5 + c];
+      out[P_BNR_G + c] = gsum[10 + c];
+      out[P_BN1_B + c] = gsum[16 + c];
+      out[P_BN1_G + c] = gsum[21 + c];
     }
+#ifdef SSTG_PHASE_CLOCKS
+    if (tid == 0) g_phase_st[blockIdx.x * 24 + 11] = clock64();
+#endif
   }
 }
 
@@ -558,6 +612,8 @@ nll_fwd_bwd_kernel(const float* __restrict__ Vpred, const float* __restrict__ Vt
                    float* __restrict__ loss, float* __restrict__ dV) {
   __shared__ float part[T_PRED];
   const int t = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  pdl_wait();
+  pdl_release();
   for (int s = blockIdx.x; s < S; s += gridDim.x) {
     const int n0 = seg_off[s], N = seg_off[s + 1] - n0;
     const float* vp = Vpred + static_cast<size_t>(n0) * 60;
@@ -623,20 +679,22 @@ __device__ __forceinline__ void bn_running_update_body(const float* __restrict__
   // tile of per-scene statistics (and element counts) in shared memory with coalesced loads, then
   // 30 threads run the recurrence over the tile out of shared memory.
   __shared__ double st[BN_TILE * SSTG_N_BN];  // momentum * (mean | unbiased variance), ready for the recurrence
+  __shared__ double fac[BN_TILE];             // momentum * M / (M - 1) of each staged scene
   const int i = threadIdx.x;
   double r = i < SSTG_N_BN ? static_cast<double>(bn[i]) : 0.0;
   for (int s0 = 0; s0 < S; s0 += BN_TILE) {
     const int ns = (S - s0 < BN_TILE) ? (S - s0) : BN_TILE;
-    // all threads: load, apply the unbiased-variance factor M / (M - 1) (the fp64 division is the expensive
-    // part -- done here in parallel, not inside the sequential recurrence) and the momentum
+    // the unbiased-variance factor M / (M - 1): ONE fp64 division per scene, by one thread per scene (the
+    // division is the expensive part; it is neither inside the sequential recurrence nor repeated per channel)
+    if (i < ns) {
+      const double M = static_cast<double>(T_OBS) * (seg_off[s0 + i + 1] - seg_off[s0 + i]);
+      fac[i] = momentum * (M / (M - 1.0));
+    }
+    __syncthreads();
     for (int j = threadIdx.x; j < ns * SSTG_N_BN; j += blockDim.x) {
       const int s = j / SSTG_N_BN, k = j - s * SSTG_N_BN;
-      double v = stats[static_cast<size_t>(s0) * SSTG_N_BN + j];
-      if ((k / 5) & 1) {
-        const double M = static_cast<double>(T_OBS) * (seg_off[s0 + s + 1] - seg_off[s0 + s]);
-        v = v * M / (M - 1.0);
-      }
-      st[j] = momentum * v;
+      const double v = stats[static_cast<size_t>(s0) * SSTG_N_BN + j];
+      st[j] = ((k / 5) & 1) ? fac[s] * v : momentum * v;
     }
     __syncthreads();
     if (i < SSTG_N_BN) {
@@ -659,16 +717,23 @@ bn_running_update_kernel(const float* __restrict__ stats, const int32_t* __restr
 
 // grad[i] = sum over CTA rows (ascending) of the two partial buffers; parameters that are
 // never executed (tpcnns.4, prelus.4 -- model.py:191) get zero.
-// ascending-row sum of one column; the loads of 8 rows are in flight together, the additions stay in order
+// ascending-row sum of one column; the loads of 16 rows are in flight together, the additions stay in order
 __device__ __forceinline__ float column_sum(const float* __restrict__ p, int rows, int stride) {
   float s = 0.f;
   int r = 0;
-  for (; r + 8 <= rows; r += 8) {
-    float v[8];
+  for (; r + 16 <= rows; r += 16) {
+    float v[16];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = __ldg(p + static_cast<size_t>(r + j) * stride);
+    for (int j = 0; j < 16; ++j) v[j] = __ldg(p + static_cast<size_t>(r + j) * stride);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) s += v[j];
+    for (int j = 0; j < 16; ++j) s += v[j];
+  }
+  for (; r + 4 <= rows; r += 4) {
+    float v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j] = __ldg(p + static_cast<size_t>(r + j) * stride);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) s += v[j];
   }
   for (; r < rows; ++r) s += __ldg(p + static_cast<size_t>(r) * stride);
   return s;
@@ -740,6 +805,7 @@ train_tail_kernel(const float* __restrict__ part_st, int rows_st, const float* _
                   const float* __restrict__ stats, const int32_t* __restrict__ seg_off, int S, double momentum,
                   float* __restrict__ bn, const float* __restrict__ loss, const float* __restrict__ weight,
                   float* __restrict__ group_loss) {
+  pdl_wait();  // writes `params`: never releases its dependents early
   if (blockIdx.x < TAIL_FIN_CTAS) {
     const int i = blockIdx.x * 256 + threadIdx.x;
     if (i >= SSTG_N_PARAMS) return;
@@ -757,7 +823,7 @@ size_t train_fwd_smem(int NP) {
   return ((sizeof(TrainParams) + 15) & ~size_t(15)) + sizeof(float) * (R_WARPS * 10 + R_WARPS * NP * 8 + C * T_OBS * NP);
 }
 size_t train_bwd_smem(int NP) {
-  return ((sizeof(TrainParams) + 15) & ~size_t(15)) + sizeof(float) * (R_WARPS * 100 + 144 + 3 * C * T_OBS * NP);
+  return ((sizeof(TrainParams) + 15) & ~size_t(15)) + sizeof(float) * (R_WARPS * 128 + 144 + 3 * C * T_OBS * NP);
 }
 
 template <int NJ>
@@ -769,12 +835,18 @@ int launch_train_fwd_nj(const float* V, const float* A, const int32_t* seg_off, 
   if (smem > 48 * 1024)
     SSTG_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)),
                   "stgcn_train_fwd smem attr");
-  kern<<<grid, R_THREADS, smem, st>>>(V, A, seg_off, a_off, S, NP, params, Y, Z, H, stats);
-  SSTG_CUDA_TRY(cudaGetLastError(), "stgcn_train_fwd launch");
+  SSTG_CUDA_TRY(launch_pdl(kern, grid, R_THREADS, smem, st, V, A, seg_off, a_off, S, NP, params, Y, Z, H, stats),
+                "stgcn_train_fwd launch");
   return SSTG_OK;
 }
 
 }  // namespace
+
+#ifdef SSTG_PHASE_CLOCKS
+extern "C" int sstg_debug_phase_clocks_st(long long* host_out, int n) {
+  return cudaMemcpyFromSymbol(host_out, g_phase_st, sizeof(long long) * (n < 300 * 24 ? n : 300 * 24)) == cudaSuccess ? 0 : -3;
+}
+#endif
 
 int train_grid(int S) {
   int dev = 0, sms = 148;
@@ -808,8 +880,9 @@ int launch_stgcn_train_backward(const float* V, const float* A, const int32_t* s
   if (smem > 48 * 1024)
     SSTG_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)),
                   "stgcn_train_bwd smem attr");
-  kern<<<train_grid(S), R_THREADS, smem, st>>>(V, A, seg_off, a_off, S, NP, params, Y, Z, stats, dH, partial);
-  SSTG_CUDA_TRY(cudaGetLastError(), "stgcn_train_bwd launch");
+  SSTG_CUDA_TRY(launch_pdl(kern, train_grid(S), R_THREADS, smem, st, V, A, seg_off, a_off, S, NP, params, Y, Z, stats,
+                           dH, partial),
+                "stgcn_train_bwd launch");
   return SSTG_OK;
 }
 
@@ -817,8 +890,9 @@ int launch_nll_fwd_bwd(const float* Vpred, const float* Vtr, const int32_t* seg_
                        float* loss, float* dV, cudaStream_t st) {
   if (S == 0) return SSTG_OK;
   const int cap = 8 * 148;
-  nll_fwd_bwd_kernel<<<S < cap ? S : cap, NLL_THREADS, 0, st>>>(Vpred, Vtr, seg_off, S, weight, loss, dV);
-  SSTG_CUDA_TRY(cudaGetLastError(), "nll_fwd_bwd launch");
+  SSTG_CUDA_TRY(launch_pdl(nll_fwd_bwd_kernel, S < cap ? S : cap, NLL_THREADS, 0, st, Vpred, Vtr, seg_off, S, weight,
+                           loss, dV),
+                "nll_fwd_bwd launch");
   return SSTG_OK;
 }
 
@@ -842,9 +916,9 @@ int launch_train_tail(const float* part_st, int rows_st, const float* part_tx, i
                       float* grad, float* params, float lr, const float* stats, const int32_t* seg_off, int S,
                       double momentum, float* bn, const float* loss, const float* weight, float* group_loss,
                       cudaStream_t st) {
-  train_tail_kernel<<<TAIL_FIN_CTAS + 2, 256, 0, st>>>(part_st, rows_st, part_tx, rows_tx, tx_stride, grad, params, lr,
-                                                      stats, seg_off, S, momentum, bn, loss, weight, group_loss);
-  SSTG_CUDA_TRY(cudaGetLastError(), "train_tail launch");
+  SSTG_CUDA_TRY(launch_pdl(train_tail_kernel, TAIL_FIN_CTAS + 2, 256, 0, st, part_st, rows_st, part_tx, rows_tx,
+                           tx_stride, grad, params, lr, stats, seg_off, S, momentum, bn, loss, weight, group_loss),
+                "train_tail launch");
   return SSTG_OK;
 }
 

@@ -229,6 +229,8 @@ txpcnn_bwd_kernel(const float* __restrict__ dOut, const float* __restrict__ Usav
   if (tid < 4) sm.slope[tid] = params[P_PRELUS + tid];
   for (int i = tid; i < B_GRAD_STRIDE; i += X_THREADS) gacc[i] = 0.f;
   float dsl[4] = {0.f, 0.f, 0.f, 0.f};
+  pdl_wait();  // everything above read only `params`
+  pdl_release();
 
 #ifdef SSTG_PHASE_CLOCKS
   if (threadIdx.x == 0) g_phase[blockIdx.x * 40 + 39] = clock64();
@@ -291,29 +293,18 @@ txpcnn_bwd_kernel(const float* __restrict__ dOut, const float* __restrict__ Usav
             DU[((half * 6 + co) * 5 + h) * Wp + sc[u]] = (co & 1) ? G[u][co >> 1][h].y : G[u][co >> 1][h].x;
       }
     }
-    // activation planes -> XT: `rows` rows of a [rows][N] block per scene; 4 loads in flight per thread
-    auto fill_xt = [&](const float* __restrict__ xb, int rows) {
+    // activation planes -> XT: `rows` rows of a [rows][N] block per scene, as 4-byte cp.async: the copies
+    // of layer l-1's input run underneath layer l's transposed convolution (which reads DU only)
+    auto fill_xt_async = [&](const float* __restrict__ xb, int rows) {
       const int n = rows * cols;
-      for (int i0 = tid; i0 < n; i0 += 4 * X_THREADS) {
-        float v[4];
-        int dst[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int i = i0 + j * X_THREADS;
-          dst[j] = -1;
-          if (i < n) {
-            const int row = i / cols, q = i - row * cols;
-            const int sb = sm.sbase[q];
-            dst[j] = row * Wp + sm.scol[q];
-            v[j] = __ldg(xb + sb * rows + (q - sb) + row * sm.nstr[q]);
-          }
-        }
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-          if (dst[j] >= 0) XT[dst[j]] = v[j];
+      for (int i = tid; i < n; i += X_THREADS) {
+        const int row = i / cols, q = i - row * cols;
+        const int sb = sm.sbase[q];
+        cp_async4(XT + row * Wp + sm.scol[q], xb + sb * rows + (q - sb) + row * sm.nstr[q]);
       }
     };
-    fill_xt(Xsave + 3 * layer_stride + static_cast<long long>(p_lo) * 60, 60);  // x4
+    fill_xt_async(Xsave + 3 * layer_stride + static_cast<long long>(p_lo) * 60, 60);  // x4
+    cp_async_wait_all();
     __syncthreads();
     PHASE(2);
 
@@ -337,6 +328,13 @@ txpcnn_bwd_kernel(const float* __restrict__ dOut, const float* __restrict__ Usav
         if (lane == 0) gacc[b_base(l) - P_TP0_W + co] += sb_;
       }
       PHASE(4 + (4 - l) * 6);
+      if (l > 0) {
+        __syncthreads();  // every read of XT (= x_l) is done: the next layer's input may land
+        if (l >= 2)
+          fill_xt_async(Xsave + (l - 2) * layer_stride + static_cast<long long>(p_lo) * 60, 60);
+        else
+          fill_xt_async(Hin + static_cast<long long>(p_lo) * 40, 40);
+      }
       // ---- transposed convolution: T = conv_l^T(du_l)
       float2 T[JX][3][5];
 #pragma unroll
@@ -368,7 +366,7 @@ txpcnn_bwd_kernel(const float* __restrict__ dOut, const float* __restrict__ Usav
         }
       }
       PHASE(5 + (4 - l) * 6);
-      __syncthreads();  // every read of DU / XT for layer l is done
+      __syncthreads();  // every read of DU for layer l is done
       PHASE(6 + (4 - l) * 6);
       if (l == 0) {
 #pragma unroll
@@ -417,10 +415,7 @@ txpcnn_bwd_kernel(const float* __restrict__ dOut, const float* __restrict__ Usav
           }
       }
       PHASE(7 + (4 - l) * 6);
-      if (k >= 1)
-        fill_xt(Xsave + (k - 1) * layer_stride + static_cast<long long>(p_lo) * 60, 60);
-      else
-        fill_xt(Hin + static_cast<long long>(p_lo) * 40, 40);
+      cp_async_wait_all();
       PHASE(8 + (4 - l) * 6);
       __syncthreads();
     }
@@ -471,9 +466,9 @@ int launch_txpcnn_backward(const float* dOut, const float* Usave, const float* X
   auto launch = [&](auto kern) -> int {
     SSTG_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)),
                   "txpcnn_bwd smem attr");
-    kern<<<grid, X_THREADS, smem, st>>>(dOut, Usave, Xsave, layer_stride, H, seg_off, tile_off, n_tiles, Wp, params,
-                                        dH, partial);
-    SSTG_CUDA_TRY(cudaGetLastError(), "txpcnn_bwd launch");
+    SSTG_CUDA_TRY(launch_pdl(kern, grid, X_THREADS, smem, st, dOut, Usave, Xsave, layer_stride, H, seg_off, tile_off,
+                             n_tiles, Wp, params, dH, partial),
+                  "txpcnn_bwd launch");
     return SSTG_OK;
   };
   if (max_n > X_COLS) return launch(txpcnn_bwd_kernel<2>);

@@ -50,28 +50,41 @@ txpcnn_fwd_kernel(const float* __restrict__ Hin, const int32_t* __restrict__ seg
   float* act = reinterpret_cast<float*>(smem_raw + ((sizeof(XSmem) + 15) & ~size_t(15)));  // [60][Wp]
   const int tid = threadIdx.x;
   const int half = tid / X_COLS;  // warp-uniform
-  const int qt = tid - half * X_COLS;
+  const int idx = tid - half * X_COLS;
 
-  // ---- weights: params [co][ci][3][3] -> shared [layer][ci][half][tap][co%6]  (tap-major for FFMA2 pairs)
-  for (int i = tid; i < X_WTOTAL; i += X_THREADS) {
-    int l, r;
-    if (i < X_W0) {
-      l = 0;
-      r = i;
-    } else {
-      l = 1 + (i - X_W0) / X_WL;
-      r = (i - X_W0) % X_WL;
+  // ---- weights: params [co][ci][3][3] -> shared [layer][ci][half][tap][co%6]  (tap-major for FFMA2 pairs);
+  //      the loads of a batch are all issued before its first store (one L2 round trip per batch)
+  constexpr int W_BATCH = 5;
+  for (int i0 = tid; i0 < X_WTOTAL; i0 += W_BATCH * X_THREADS) {
+    float v[W_BATCH];
+#pragma unroll
+    for (int j = 0; j < W_BATCH; ++j) {
+      const int i = i0 + j * X_THREADS;
+      v[j] = 0.f;
+      if (i < X_WTOTAL) {
+        int l, r;
+        if (i < X_W0) {
+          l = 0;
+          r = i;
+        } else {
+          l = 1 + (i - X_W0) / X_WL;
+          r = (i - X_W0) % X_WL;
+        }
+        const int ci = r / (2 * X_WSLOT), r2 = r % (2 * X_WSLOT);
+        const int hf = r2 / X_WSLOT, r3 = r2 % X_WSLOT;
+        if (r3 < 54) {
+          const int co = hf * 6 + r3 % 6, tap = r3 / 6;
+          const int cin = (l == 0) ? 8 : 12;
+          const int base = (l == 0) ? P_TP0_W : (l == 4 ? P_TPOUT_W : P_TP1_W + (l - 1) * P_TP_STRIDE);
+          v[j] = __ldg(params + base + (co * cin + ci) * 9 + tap);
+        }
+      }
     }
-    const int ci = r / (2 * X_WSLOT), r2 = r % (2 * X_WSLOT);
-    const int hf = r2 / X_WSLOT, r3 = r2 % X_WSLOT;
-    float v = 0.f;
-    if (r3 < 54) {
-      const int co = hf * 6 + r3 % 6, tap = r3 / 6;
-      const int cin = (l == 0) ? 8 : 12;
-      const int base = (l == 0) ? P_TP0_W : (l == 4 ? P_TPOUT_W : P_TP1_W + (l - 1) * P_TP_STRIDE);
-      v = params[base + (co * cin + ci) * 9 + tap];
+#pragma unroll
+    for (int j = 0; j < W_BATCH; ++j) {
+      const int i = i0 + j * X_THREADS;
+      if (i < X_WTOTAL) sm.w[i] = v[j];
     }
-    sm.w[i] = v;
   }
   if (tid < 60) {
     const int l = tid / 12, co = tid % 12;
@@ -79,11 +92,19 @@ txpcnn_fwd_kernel(const float* __restrict__ Hin, const int32_t* __restrict__ seg
     sm.bias[l][co] = params[base + co];
   }
   if (tid < 4) sm.slope[tid] = params[P_PRELUS + tid];
+  pdl_wait();  // everything above read only `params`
+  pdl_release();
 
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const int s_lo = tile_off[tile], s_hi = tile_off[tile + 1];
     const int p_lo = seg_off[s_lo];
     const int cols = seg_off[s_hi] - p_lo;
+    // Training tiles are small (one ~10-pedestrian scene per CTA) and the step is latency-bound: a tile of
+    // <= 64 columns spreads each column's convolution over 2 or 4 lanes (slices of the input channels,
+    // butterfly-summed so that all lanes of a column hold the same bits).  CTA-uniform.
+    const int cgs = !SAVE ? 1 : (cols <= X_COLS / 4 ? 4 : (cols <= X_COLS / 2 ? 2 : 1));
+    const int qt = cgs == 4 ? (idx >> 2) : (cgs == 2 ? (idx >> 1) : idx);
+    const int cg = idx & (cgs - 1);
     __syncthreads();  // previous tile fully written out / weights visible
     // ---- column tables + zero separator columns
     for (int q = tid; q < cols; q += X_THREADS) {
@@ -136,15 +157,43 @@ txpcnn_fwd_kernel(const float* __restrict__ Hin, const int32_t* __restrict__ seg
       for (int u = 0; u < JX; ++u) {
 #pragma unroll
         for (int pr = 0; pr < 3; ++pr) {
-          const float2 b = make_float2(sm.bias[l][half * 6 + 2 * pr], sm.bias[l][half * 6 + 2 * pr + 1]);
+          float2 b = make_float2(sm.bias[l][half * 6 + 2 * pr], sm.bias[l][half * 6 + 2 * pr + 1]);
+          if (cg != 0) b = make_float2(0.f, 0.f);  // the bias enters the butterfly sum once
 #pragma unroll
           for (int h = 0; h < 5; ++h) acc[u][pr][h] = b;
         }
-        if (on[u]) {
-          if (l == 0)
-            conv_column2<8>(act, Wp, sc[u], wl, half, acc[u]);
-          else
-            conv_column2<12>(act, Wp, sc[u], wl, half, acc[u]);
+        if (!SAVE || cgs == 1) {
+          if (on[u]) {
+            if (l == 0)
+              conv_column2<8>(act, Wp, sc[u], wl, half, acc[u]);
+            else
+              conv_column2<12>(act, Wp, sc[u], wl, half, acc[u]);
+          }
+        } else {
+          if (on[u]) {
+            if (cgs == 4) {
+              if (l == 0)
+                conv_column2<2>(act, Wp, sc[u], wl, half, acc[u], cg * 2);
+              else
+                conv_column2<3>(act, Wp, sc[u], wl, half, acc[u], cg * 3);
+            } else {
+              if (l == 0)
+                conv_column2<4>(act, Wp, sc[u], wl, half, acc[u], cg * 4);
+              else
+                conv_column2<6>(act, Wp, sc[u], wl, half, acc[u], cg * 6);
+            }
+          }
+#pragma unroll
+          for (int pr = 0; pr < 3; ++pr)
+#pragma unroll
+            for (int h = 0; h < 5; ++h) {
+              acc[u][pr][h].x += __shfl_xor_sync(0xffffffffu, acc[u][pr][h].x, 1);
+              acc[u][pr][h].y += __shfl_xor_sync(0xffffffffu, acc[u][pr][h].y, 1);
+              if (cgs == 4) {
+                acc[u][pr][h].x += __shfl_xor_sync(0xffffffffu, acc[u][pr][h].x, 2);
+                acc[u][pr][h].y += __shfl_xor_sync(0xffffffffu, acc[u][pr][h].y, 2);
+              }
+            }
         }
       }
       if (l < 4) {
@@ -161,7 +210,7 @@ txpcnn_fwd_kernel(const float* __restrict__ Hin, const int32_t* __restrict__ seg
                 const int row = (half * 6 + 2 * pr + e) * 5 + h;
                 float v = prelu(a, sl);
                 if (l > 0) v += act[row * Wp + sc[u]];  // residual (model.py:192)
-                if (SAVE && on[u]) {
+                if (SAVE && on[u] && cg == 0) {
                   const long long g = l * layer_stride + gO[u] + static_cast<long long>(row) * gN[u];
                   Usave[g] = a;
                   Xsave[g] = v;
@@ -183,7 +232,7 @@ txpcnn_fwd_kernel(const float* __restrict__ Hin, const int32_t* __restrict__ seg
       } else {
 #pragma unroll
         for (int u = 0; u < JX; ++u)
-          if (on[u]) {
+          if (on[u] && cg == 0) {
             float* o = out + gO[u];
 #pragma unroll
             for (int pr = 0; pr < 3; ++pr)
@@ -231,6 +280,12 @@ int launch_txpcnn_forward(const float* H, const int32_t* seg_off, const int32_t*
     if (per_sm < 1) per_sm = 1;
     const long long want = static_cast<long long>(sms) * per_sm;
     const int grid = static_cast<int>(n_tiles < want ? n_tiles : want);
+    if (save) {
+      SSTG_CUDA_TRY(launch_pdl(kern, grid, X_THREADS, smem, st, H, seg_off, tile_off, n_tiles, Wp, params, out, Usave,
+                               Xsave, layer_stride),
+                    "txpcnn launch");
+      return SSTG_OK;
+    }
     kern<<<grid, X_THREADS, smem, st>>>(H, seg_off, tile_off, n_tiles, Wp, params, out, Usave, Xsave, layer_stride);
     SSTG_CUDA_TRY(cudaGetLastError(), "txpcnn launch");
     return SSTG_OK;
