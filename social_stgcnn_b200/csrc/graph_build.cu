@@ -66,6 +66,8 @@ graph_build_kernel(const float* __restrict__ rel, const int32_t* __restrict__ se
   Real* dsw = reinterpret_cast<Real*>(ys + T * NP) + (threadIdx.x >> 5) * NP;  // [warp][NP]
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  pdl_wait();     // first kernels of the training chain: the launch overlaps the predecessor's tail
+  pdl_release();
   const bool norm_lap = flags & SSTG_GRAPH_NORM_LAP;
   const bool v_only = flags & SSTG_GRAPH_V_ONLY;
 
@@ -204,6 +206,8 @@ graph_build_fast_kernel(const float* __restrict__ rel, const int32_t* __restrict
   float* dsm = ys + F_WARPS * NP;                   // [4][NP]
   float* Wt = dsm + F_WARPS * NP + static_cast<size_t>(threadIdx.x >> 5) * wtile;  // [warp][N*N]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  pdl_wait();
+  pdl_release();
   const int groups = T / F_WARPS;
   const long long items = static_cast<long long>(S) * groups;
 
@@ -397,8 +401,8 @@ int launch_fast(const float* rel, const int32_t* seg_off, const int64_t* a_off, 
   const long long items = static_cast<long long>(S) * (T / F_WARPS);
   const long long want = static_cast<long long>(sms) * per_sm;
   const int grid = static_cast<int>(items < want ? items : want);
-  kern<<<grid, F_THREADS, smem, st>>>(rel, seg_off, a_off, S, T, NP, wtile, V, A);
-  SSTG_CUDA_TRY(cudaGetLastError(), "graph_build_fast launch");
+  SSTG_CUDA_TRY(launch_pdl(kern, grid, F_THREADS, smem, st, rel, seg_off, a_off, S, T, NP, wtile, V, A),
+                "graph_build_fast launch");
   return SSTG_OK;
 }
 
@@ -419,8 +423,8 @@ int launch_nj(const float* rel, const int32_t* seg_off, const int64_t* a_off, in
   if (per_sm < 1) per_sm = 1;
   const long long want = static_cast<long long>(sms) * per_sm;
   const int grid = static_cast<int>(S < want ? S : want);
-  kern<<<grid, G_THREADS, smem, st>>>(rel, seg_off, a_off, S, T, NP, V, A, flags);
-  SSTG_CUDA_TRY(cudaGetLastError(), "graph_build launch");
+  SSTG_CUDA_TRY(launch_pdl(kern, grid, G_THREADS, smem, st, rel, seg_off, a_off, S, T, NP, V, A, flags),
+                "graph_build launch");
   return SSTG_OK;
 }
 

@@ -20,9 +20,10 @@
 // Small tiles (the reference's optimiser groups are ~128 scenes of ~10 pedestrians: one scene per CTA,
 // the step is LATENCY-bound): a tile of <= 64 columns spreads each column's transposed convolution over
 // 2 or 4 lanes (slices of the 12 channels, butterfly-summed so all lanes hold the same bits), gives every
-// (output channel, input channel) weight-gradient unit to ONE thread (9 taps in registers, columns in
-// ascending order, no reduction at all), and every global load phase issues all its loads before the
-// first use.
+// (output-channel pair, input channel) weight-gradient unit to a trio of lanes that split the columns
+// (packed accumulators, two shuffles per value to combine), issues all loads of a global-load phase
+// before their first use, and brings the next layer's activations in with cp.async underneath the
+// transposed convolution.
 #include "txpcnn_common.cuh"
 
 namespace sstg {
@@ -140,27 +141,40 @@ __device__ __forceinline__ void dw_unit(const float* __restrict__ DU, const floa
   }
 }
 
-// Small tile: thread `unit` owns dW[co][ci][0..8]; it walks the tile's columns in ascending order with a
-// sliding 5x3 window of x, so the sum order is fixed and no cross-lane reduction is needed.
-__device__ __forceinline__ void dw_unit_thread(const float* __restrict__ DU, const float* __restrict__ XT, int Wp,
-                                               int c_end, int co, int ci, int cin, float* __restrict__ gw) {
-  float acc[9];
+// Small tile (<= 64 columns): three adjacent lanes own one (output-channel PAIR, input channel) unit and a
+// third of the tile's columns each; a lane walks its columns in ascending order with a sliding 5x3 window
+// of x and 9 packed accumulators (18 weight gradients), the three slices are added in slice order through
+// two shuffles per value, and lane 0 of the trio updates the CTA accumulator entries only it ever touches.
+// 10 trios per warp, 8 warps: 72 units (12 input channels) in one pass.
+__device__ __forceinline__ void dw_pair_slices(const float* __restrict__ DU, const float* __restrict__ XT, int Wp,
+                                               int c_end, int cin, int warp, int lane, float* __restrict__ gw) {
+  const int grp = lane / 3, sl = lane - grp * 3;
+  const int pu = warp * 10 + grp;
+  const bool act = lane < 30 && pu < 6 * cin;
+  const int p = act ? pu / cin : 0, ci = act ? pu - p * cin : 0;
+  const int per = (c_end + 2) / 3;
+  const int c_lo = 1 + sl * per;
+  int c_hi = c_lo + per - 1;
+  if (c_hi > c_end) c_hi = c_end;
+  if (!act) c_hi = 0;
+  float2 acc[9];
 #pragma unroll
-  for (int k = 0; k < 9; ++k) acc[k] = 0.f;
+  for (int k = 0; k < 9; ++k) acc[k] = make_float2(0.f, 0.f);
   const float* xr = XT + (ci * 5) * Wp;
-  const float* dr = DU + (co * 5) * Wp;
+  const float* d0 = DU + ((2 * p) * 5) * Wp;
+  const float* d1 = d0 + 5 * Wp;
   float x0[5], x1[5], x2[5];
 #pragma unroll
   for (int h = 0; h < 5; ++h) {
-    x0[h] = xr[h * Wp];      // column 0 is a zero separator
-    x1[h] = xr[h * Wp + 1];
+    x0[h] = xr[h * Wp + c_lo - 1];
+    x1[h] = xr[h * Wp + c_lo];
   }
-  for (int c = 1; c <= c_end; ++c) {
-    float d[5];
+  for (int c = c_lo; c <= c_hi; ++c) {
+    float2 d[5];
 #pragma unroll
     for (int h = 0; h < 5; ++h) {
       x2[h] = xr[h * Wp + c + 1];
-      d[h] = dr[h * Wp + c];
+      d[h] = make_float2(d0[h * Wp + c], d1[h * Wp + c]);
     }
 #pragma unroll
     for (int kh = 0; kh < 3; ++kh)
@@ -168,9 +182,9 @@ __device__ __forceinline__ void dw_unit_thread(const float* __restrict__ DU, con
       for (int h = 0; h < 5; ++h) {
         const int hi = h + kh - 1;
         if (hi >= 0 && hi < 5) {
-          acc[kh * 3 + 0] = fmaf(d[h], x0[hi], acc[kh * 3 + 0]);
-          acc[kh * 3 + 1] = fmaf(d[h], x1[hi], acc[kh * 3 + 1]);
-          acc[kh * 3 + 2] = fmaf(d[h], x2[hi], acc[kh * 3 + 2]);
+          ffma2(acc[kh * 3 + 0], d[h], make_float2(x0[hi], x0[hi]));
+          ffma2(acc[kh * 3 + 1], d[h], make_float2(x1[hi], x1[hi]));
+          ffma2(acc[kh * 3 + 2], d[h], make_float2(x2[hi], x2[hi]));
         }
       }
 #pragma unroll
@@ -179,9 +193,17 @@ __device__ __forceinline__ void dw_unit_thread(const float* __restrict__ DU, con
       x1[h] = x2[h];
     }
   }
-  float* g = gw + (co * cin + ci) * 9;
+  float* g0 = gw + ((2 * p) * cin + ci) * 9;
+  float* g1 = g0 + cin * 9;
 #pragma unroll
-  for (int k = 0; k < 9; ++k) g[k] += acc[k];
+  for (int k = 0; k < 9; ++k) {
+    const float ax = (acc[k].x + __shfl_down_sync(0xffffffffu, acc[k].x, 1)) + __shfl_down_sync(0xffffffffu, acc[k].x, 2);
+    const float ay = (acc[k].y + __shfl_down_sync(0xffffffffu, acc[k].y, 1)) + __shfl_down_sync(0xffffffffu, acc[k].y, 2);
+    if (act && sl == 0) {
+      g0[k] += ax;
+      g1[k] += ay;
+    }
+  }
 }
 
 template <int JX>
@@ -295,13 +317,17 @@ txpcnn_bwd_kernel(const float* __restrict__ dOut, const float* __restrict__ Usav
     }
     // activation planes -> XT: `rows` rows of a [rows][N] block per scene, as 4-byte cp.async: the copies
     // of layer l-1's input run underneath layer l's transposed convolution (which reads DU only)
+    // thread = (column q, row phase): a row of the tile takes 32/64/128/256 lanes (the smallest that covers
+    // `cols`), so no index division and the per-copy address is one add
+    const int lpr_log = cols <= 32 ? 5 : (cols <= 64 ? 6 : (cols <= 128 ? 7 : 8));
+    const int fq = tid & ((1 << lpr_log) - 1), frow0 = tid >> lpr_log, frstep = X_THREADS >> lpr_log;
+    const bool fon = fq < cols;
+    const int fdst = fon ? sm.scol[fq] : 0, fns = fon ? sm.nstr[fq] : 0, fsb = fon ? sm.sbase[fq] : 0;
     auto fill_xt_async = [&](const float* __restrict__ xb, int rows) {
-      const int n = rows * cols;
-      for (int i = tid; i < n; i += X_THREADS) {
-        const int row = i / cols, q = i - row * cols;
-        const int sb = sm.sbase[q];
-        cp_async4(XT + row * Wp + sm.scol[q], xb + sb * rows + (q - sb) + row * sm.nstr[q]);
-      }
+      if (!fon) return;
+      const float* src = xb + fsb * rows + (fq - fsb) + frow0 * fns;
+      float* dst = XT + frow0 * Wp + fdst;
+      for (int row = frow0; row < rows; row += frstep, src += frstep * fns, dst += frstep * Wp) cp_async4(dst, src);
     };
     fill_xt_async(Xsave + 3 * layer_stride + static_cast<long long>(p_lo) * 60, 60);  // x4
     cp_async_wait_all();
@@ -315,7 +341,7 @@ txpcnn_bwd_kernel(const float* __restrict__ dOut, const float* __restrict__ Usav
       // ---- weight and bias gradients of layer l
       float* gw = gacc + (w_base(l) - P_TP0_W);
       if (cgs > 1) {
-        if (tid < 12 * cin) dw_unit_thread(DU, XT, Wp, c_end, tid / cin, tid % cin, cin, gw);
+        dw_pair_slices(DU, XT, Wp, c_end, cin, warp, lane, gw);
       } else {
         for (int unit = warp; unit < 2 * cin; unit += 8) dw_unit(DU, XT, Wp, c_end, unit >> 1, unit & 1, cin, lane, gw);
       }

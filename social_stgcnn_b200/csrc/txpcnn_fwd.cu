@@ -36,6 +36,18 @@ namespace {
 
 using namespace txp;
 
+// -DSSTG_PHASE_CLOCKS: thread 0 of every CTA stamps clock64() at the phase boundaries of its first tile
+// (profiling aid for the latency-bound small-group case; read back with sstg_debug_phase_clocks_xf).
+#ifdef SSTG_PHASE_CLOCKS
+__device__ long long g_phase_xf[160 * 16];
+#define PHASE_XF(k)                                                                                      \
+  do {                                                                                                   \
+    if (threadIdx.x == 0 && tile == static_cast<int>(blockIdx.x)) g_phase_xf[blockIdx.x * 16 + (k)] = clock64(); \
+  } while (0)
+#else
+#define PHASE_XF(k)
+#endif
+
 // SAVE (training): also store every layer's pre-activation u_l = conv_l(x_l) and its output
 // x_{l+1} (l = 0..3) for the backward pass, in the same (12,5,N)-rows-per-scene layout as
 // `out`, layer l at float offset l * layer_stride.
@@ -51,6 +63,9 @@ txpcnn_fwd_kernel(const float* __restrict__ Hin, const int32_t* __restrict__ seg
   const int tid = threadIdx.x;
   const int half = tid / X_COLS;  // warp-uniform
   const int idx = tid - half * X_COLS;
+#ifdef SSTG_PHASE_CLOCKS
+  if (tid == 0) g_phase_xf[blockIdx.x * 16 + 0] = clock64();
+#endif
 
   // ---- weights: params [co][ci][3][3] -> shared [layer][ci][half][tap][co%6]  (tap-major for FFMA2 pairs);
   //      the loads of a batch are all issued before its first store (one L2 round trip per batch)
@@ -96,6 +111,7 @@ txpcnn_fwd_kernel(const float* __restrict__ Hin, const int32_t* __restrict__ seg
   pdl_release();
 
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    PHASE_XF(1);
     const int s_lo = tile_off[tile], s_hi = tile_off[tile + 1];
     const int p_lo = seg_off[s_lo];
     const int cols = seg_off[s_hi] - p_lo;
@@ -134,6 +150,7 @@ txpcnn_fwd_kernel(const float* __restrict__ Hin, const int32_t* __restrict__ seg
     }
     cp_async_wait_all();
     __syncthreads();
+    PHASE_XF(2);
 
     int sc[JX], gN[JX];
     long long gO[JX];  // float offset of (row 0, this column) in a 60-rows-per-scene buffer
@@ -196,6 +213,7 @@ txpcnn_fwd_kernel(const float* __restrict__ Hin, const int32_t* __restrict__ seg
             }
         }
       }
+      PHASE_XF(3 + 2 * l);
       if (l < 4) {
         const float sl = sm.slope[l];
 #pragma unroll
@@ -229,6 +247,7 @@ txpcnn_fwd_kernel(const float* __restrict__ Hin, const int32_t* __restrict__ seg
                 act[((half * 6 + 2 * pr + 1) * 5 + h) * Wp + sc[u]] = acc[u][pr][h].y;
               }
         __syncthreads();
+        PHASE_XF(4 + 2 * l);
       } else {
 #pragma unroll
         for (int u = 0; u < JX; ++u)
@@ -242,12 +261,19 @@ txpcnn_fwd_kernel(const float* __restrict__ Hin, const int32_t* __restrict__ seg
                 o[((half * 6 + 2 * pr + 1) * 5 + h) * gN[u]] = acc[u][pr][h].y;
               }
           }
+        PHASE_XF(12);
       }
     }
   }
 }
 
 }  // namespace
+
+#ifdef SSTG_PHASE_CLOCKS
+extern "C" int sstg_debug_phase_clocks_xf(long long* host_out, int n) {
+  return cudaMemcpyFromSymbol(host_out, g_phase_xf, sizeof(long long) * (n < 160 * 16 ? n : 160 * 16)) == cudaSuccess ? 0 : -3;
+}
+#endif
 
 int txpcnn_tile_width(int max_n) {
   int Wp = txp::X_COLS + SSTG_XTILE_MAX_SCENES + 1;
