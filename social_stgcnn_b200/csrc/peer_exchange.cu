@@ -221,6 +221,15 @@ int sstg_peer_exchange_apply(void* const* mailboxes, int32_t world, int32_t rank
   if (!mailboxes || !grad_local || !params || !grad_out || !status || (s_local > 0 && !stats_local)) return SSTG_EINVAL;
   if (s_all > 0 && (!stats_out || !seg_off_all || !bn)) return SSTG_EINVAL;
   if (!(bn_momentum >= 0.0 && bn_momentum <= 1.0)) return SSTG_EINVAL;
+  // Both kernels of this call are loaded BEFORE the first one is launched: CUDA's lazy loading may
+  // synchronise the context on a first launch, and with the exchange kernel already waiting for peers that
+  // would stall this rank (and deadlock ranks that share one process, as the single-GPU tests do).
+  {
+    cudaFuncAttributes fa;
+    SSTG_CUDA_TRY(cudaFuncGetAttributes(&fa, peer_exchange_sgd_kernel), "peer_exchange preload");
+    const int rc = preload_bn_running_update();
+    if (rc != SSTG_OK) return rc;
+  }
   PeerBoxes boxes;
   for (int r = 0; r < SSTG_MAX_RANKS; ++r) {
     boxes.box[r] = r < world ? static_cast<float*>(mailboxes[r]) : nullptr;

@@ -170,6 +170,7 @@ int launch_nll_fwd_bwd(const float* Vpred, const float* Vtr, const int32_t* seg_
                        float* loss, float* dV, cudaStream_t st);
 int launch_bn_running_update(const float* stats, const int32_t* seg_off, int S, double momentum, float* bn,
                              cudaStream_t st, const int32_t* abort_flag = nullptr);
+int preload_bn_running_update();
 int launch_grad_finalize(const float* part_st, int rows_st, const float* part_tx, int rows_tx, int tx_stride,
                          float* grad, cudaStream_t st);
 int launch_group_loss(const float* loss, const float* weight, int S, float* out, cudaStream_t st);

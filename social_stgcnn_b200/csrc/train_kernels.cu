@@ -896,6 +896,14 @@ int launch_nll_fwd_bwd(const float* Vpred, const float* Vtr, const int32_t* seg_
   return SSTG_OK;
 }
 
+// CUDA loads kernels lazily, and a first-time load may synchronise the context: it must not happen while
+// another kernel of this process is waiting for a peer (peer_exchange.cu) -- load ahead of time.
+int preload_bn_running_update() {
+  cudaFuncAttributes fa;
+  SSTG_CUDA_TRY(cudaFuncGetAttributes(&fa, bn_running_update_kernel), "bn_running_update preload");
+  return SSTG_OK;
+}
+
 int launch_bn_running_update(const float* stats, const int32_t* seg_off, int S, double momentum, float* bn,
                              cudaStream_t st, const int32_t* abort_flag) {
   if (S == 0) return SSTG_OK;
