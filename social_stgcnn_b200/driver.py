@@ -98,6 +98,8 @@ def train_epoch(dataset, engine: E.TrainEngine, batch_size: int = 128, lr: float
             loss_batch += trainer.step(n_all[scenes], obs, pred, batch_size, lr, clip_grad)
         else:
             loss_batch += engine.step(E.ScenePlan(n_all[scenes]), obs, pred, batch_size, lr, clip_grad).double()
+    if trainer is not None and getattr(trainer, "peer", None) is not None:
+        trainer.peer.check()            # a rank that never delivered: raise instead of training on
     return float(loss_batch) / S
 
 

@@ -106,3 +106,24 @@ def test_cpu_tensors_are_refused(lib):
         sstg.InferenceEngine(np.zeros(7563, np.float32), np.zeros(30, np.float32), "cpu")
     with pytest.raises(RuntimeError, match="CUDA"):
         sstg.ScenePlan([2, 3]).on("cpu")
+
+
+def test_peer_mailbox_and_workspace_host_arithmetic(lib):
+    """Host-only entry points of the sharded-training exchange (no GPU needed)."""
+    # mailbox = 2 parities x (world slots of 7,564 floats + stats rows) + flag words
+    b = lib.sstg_peer_mailbox_bytes(2, 128)
+    assert b == (2 * (2 * 7564 + 128 * 30) + 16) * 4
+    assert lib.sstg_peer_mailbox_bytes(8, 0) == (2 * 8 * 7564 + 16) * 4
+    assert lib.sstg_peer_mailbox_bytes(0, 4) < 0 and lib.sstg_peer_mailbox_bytes(9, 4) < 0
+    assert lib.sstg_peer_mailbox_bytes(2, -1) < 0
+    # the statistics block of sstg_train_step's workspace lies inside it, 16-byte aligned
+    total = lib.sstg_train_step_workspace(12, 5, 100, 4000)
+    off = lib.sstg_train_step_stats_offset(12, 5, 100, 4000)
+    assert 0 < off < total and off % 4 == 0 and off + 12 * 30 <= total
+    assert lib.sstg_train_step_stats_offset(-1, 0, 0, 0) < 0
+    # argument validation happens before anything touches the device
+    assert lib.sstg_peer_alloc(0, None, None) == -1
+    assert lib.sstg_peer_open(None, None) == -1
+    assert lib.sstg_peer_close(None) == 0 and lib.sstg_peer_free(None) == 0
+    assert lib.sstg_peer_exchange_apply(None, 0, 0, 1, 0, None, None, None, 0, 0, None, 0, None, None, 0.0, 0.0, 0.1,
+                                        None, None, None, None, 0, None) == -1
