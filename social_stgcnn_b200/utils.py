@@ -148,6 +148,41 @@ def load_scenes(data_dir, obs_len, pred_len, skip, threshold, min_ped, delim):
     return seqs, rels, masks, non_linear, counts, max_peds
 
 
+class _LazyPacked(dict):
+    """The dataset's packed device tensors; "A_tr" is computed the first time it is asked for."""
+
+    def __init__(self, make_a_tr, items):
+        super().__init__(items)
+        self._make_a_tr = make_a_tr
+
+    def __missing__(self, key):
+        if key != "A_tr":
+            raise KeyError(key)
+        self["A_tr"] = self._make_a_tr()
+        return dict.__getitem__(self, "A_tr")
+
+
+class _LazyAdjacencyList:
+    """`dataset.A_pred`: a list of per-scene (T_pred, N, N) views, materialised on first use."""
+
+    def __init__(self, dataset):
+        self._ds, self._views = dataset, None
+
+    def _get(self):
+        if self._views is None:
+            self._views = self._ds._pred_adjacency_views()
+        return self._views
+
+    def __getitem__(self, i):
+        return self._get()[i]
+
+    def __len__(self):
+        return self._ds.num_seq
+
+    def __iter__(self):
+        return iter(self._get())
+
+
 class TrajectoryDataset(Dataset):
     """Dataloder for the Trajectory datasets -- drop-in for utils.py:86-228."""
 
@@ -189,18 +224,39 @@ class TrajectoryDataset(Dataset):
         obs_rel_d = self.obs_traj_rel.to(dev).contiguous()
         pred_rel_d = self.pred_traj_rel.to(dev).contiguous()
         V_o, A_o = graph_build(self.plan_obs.on(dev), obs_rel_d, obs_len, norm_lap=norm_lap_matr, fp64=True)
-        V_p, A_p = graph_build(self.plan_pred.on(dev), pred_rel_d, pred_len, norm_lap=norm_lap_matr, fp64=True)
-        self.packed = {"device": dev, "obs_rel": obs_rel_d, "pred_rel": pred_rel_d, "V_obs": V_o, "A_obs": A_o,
-                       "V_tr": V_p, "A_tr": A_p, "last_obs": self.obs_traj[:, :, -1].to(dev).contiguous()}
-        V_oc, A_oc, V_pc, A_pc = V_o.cpu(), A_o.cpu(), V_p.cpu(), A_p.cpu()
-        self.v_obs, self.A_obs, self.v_pred, self.A_pred = [], [], [], []
+        # The pred-half adjacency A_tr (utils.py:209-211) is 60 % of the reference's graph work and nothing on
+        # the path consumes it: only V_tr is built here; A_tr is built on first access of
+        # `A_pred[...]`, item [9] of __getitem__, or `packed["A_tr"]`.
+        V_p, _ = graph_build(self.plan_pred.on(dev), pred_rel_d, pred_len, v_only=True)
+        self.packed = _LazyPacked(self._build_pred_adjacency,
+                                  {"device": dev, "obs_rel": obs_rel_d, "pred_rel": pred_rel_d, "V_obs": V_o,
+                                   "A_obs": A_o, "V_tr": V_p,
+                                   "last_obs": self.obs_traj[:, :, -1].to(dev).contiguous()})
+        V_oc, A_oc, V_pc = V_o.cpu(), A_o.cpu(), V_p.cpu()
+        self.v_obs, self.A_obs, self.v_pred = [], [], []
+        self._counts, self._cum = list(counts), cum
         for i, n in enumerate(counts):
             s = cum[i]
-            ao, ap = int(self.plan_obs.a_off[i]), int(self.plan_pred.a_off[i])
+            ao = int(self.plan_obs.a_off[i])
             self.v_obs.append(V_oc[s * obs_len * 2:(s + n) * obs_len * 2].view(obs_len, n, 2))
             self.A_obs.append(A_oc[ao:ao + obs_len * n * n].view(obs_len, n, n))
             self.v_pred.append(V_pc[s * pred_len * 2:(s + n) * pred_len * 2].view(pred_len, n, 2))
-            self.A_pred.append(A_pc[ap:ap + pred_len * n * n].view(pred_len, n, n))
+        self.A_pred = _LazyAdjacencyList(self)
+
+    def _build_pred_adjacency(self):
+        """A_tr of every scene, packed on the device (one launch over the whole dataset)."""
+        dev = self.packed["device"]
+        _, A_p = graph_build(self.plan_pred.on(dev), self.packed["pred_rel"], self.pred_len,
+                             norm_lap=self.norm_lap_matr, fp64=True)
+        return A_p
+
+    def _pred_adjacency_views(self):
+        A_pc = self.packed["A_tr"].cpu()
+        out = []
+        for i, n in enumerate(self._counts):
+            ap = int(self.plan_pred.a_off[i])
+            out.append(A_pc[ap:ap + self.pred_len * n * n].view(self.pred_len, n, n))
+        return out
 
     def __len__(self):
         return self.num_seq

@@ -159,13 +159,17 @@ def test_seq_to_graph_and_dataset(golden, dev):
     d = TrajectoryDataset(os.path.join(GOLD, "datasets", "eth", "test") + "/", obs_len=8, pred_len=12, skip=1,
                           norm_lap_matr=True)
     assert len(d) == 70 and d.obs_traj.shape[0] == 181
+    # the pred-half adjacency is built on first use only; V_tr is there from the start
+    assert "A_tr" not in d.packed and "V_tr" in d.packed and len(d.A_pred) == 70
     for i in range(70):
         item = d[i]
         assert len(item) == 10
+        assert "A_tr" in d.packed
         name = f"eth{i:03d}"
         assert np.array_equal(item[2].numpy(), g[f"{name}.obs_rel"]), name
         assert np.array_equal(item[6].numpy(), g[f"{name}.V_obs"]), name
         assert np.array_equal(item[7].numpy().view(np.uint32), g[f"{name}.A_obs"].view(np.uint32)), name
+        assert np.array_equal(item[8].numpy(), g[f"{name}.V_tr"]), name
         assert np.array_equal(item[9].numpy().view(np.uint32), g[f"{name}.A_tr"].view(np.uint32)), name
     with pytest.raises(ValueError):
         TrajectoryDataset(os.path.join(GOLD, "datasets", "eth", "test") + "/", obs_len=8, pred_len=12, delim=" ")
