@@ -302,7 +302,8 @@ def run_train_leg(dev, world, rank, steps, warmup, batch=128):
 
     def timed(exchange):
         eng = sstg.TrainEngine(params, bn, dev)
-        trainer = Pl.DistributedTrainer(eng, exchange=exchange, max_scenes=batch) if world > 1 else None
+        trainer = Pl.DistributedTrainer(eng, exchange=exchange, max_scenes=batch, peer_timeout_s=2.0) \
+            if world > 1 else None
 
         def one(i):
             n, plan, obs, pred = groups[i % len(groups)]
@@ -313,6 +314,14 @@ def run_train_leg(dev, world, rank, steps, warmup, batch=128):
 
         for i in range(warmup):
             one(i)
+        if trainer is not None and trainer.peer is not None:
+            # a peer that cannot be reached (IPC / peer access refused on this box) shows up here, after at most
+            # warmup x 2 s; every rank learns about it and the leg is re-timed through NCCL
+            bad = torch.tensor([int(trainer.peer.status.item() != 0)], dtype=torch.int32, device=dev)
+            dist.all_reduce(bad, op=dist.ReduceOp.MAX)
+            if int(bad[0]):
+                trainer.peer.close()
+                return None, "peer-failed"
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
@@ -334,6 +343,8 @@ def run_train_leg(dev, world, rank, steps, warmup, batch=128):
 
     ms, exchange = timed("auto")
     nccl = None
+    if exchange == "peer-failed":
+        ms, exchange = timed("nccl")
     if world > 1 and exchange == "peer":
         ms_nccl, _ = timed("nccl")
         nccl = {"value": batch * steps / (ms_nccl * 1e-3), "unit": "scenes/s", "ms_per_group": ms_nccl / steps,

@@ -294,7 +294,8 @@ class DistributedTrainer:
                "auto": "peer" when every rank is on CUDA on one node and world <= 8 (env
                        SSTG_EXCHANGE=nccl|peer overrides), else "nccl"."""
 
-    def __init__(self, engine, group=None, exchange: str = "auto", max_scenes: int = 256, *, _emulate=None):
+    def __init__(self, engine, group=None, exchange: str = "auto", max_scenes: int = 256, *,
+                 peer_timeout_s: float = 5.0, _emulate=None):
         import os
         self.engine, self.group = engine, group
         self._flat, self._groups = {}, {}
@@ -310,7 +311,7 @@ class DistributedTrainer:
         self.peer = None
         if world > 1 and world <= 8 and (mode == "peer" or (mode == "auto" and engine.device.type == "cuda")):
             try:
-                self.peer = PeerExchange(engine.device, max_scenes, group)
+                self.peer = PeerExchange(engine.device, max_scenes, group, timeout_s=peer_timeout_s)
                 ok = 1
             except Exception as e:
                 if mode == "peer":
