@@ -106,18 +106,24 @@ def test_train_group_vs_reference(golden, dev, tag):
     assert np.allclose(eng.bn.cpu().numpy(), Lz[f"train.{tag}.bn"], rtol=1e-5, atol=1e-7)
 
 
-def test_train_step_vs_fp64_oracle_ragged(golden, dev):
+@pytest.mark.parametrize("n_list", [
+    [2, 3, 33, 64, 7, 130, 5, 40],
+    # the switch points of the small-tile forms of the TXP-CNN kernels (<= 32: 4 lanes per column, <= 64: 2,
+    # above: 1; > 128: two columns per thread) and several tiny scenes sharing one tile
+    [32, 63, 65, 2, 2, 3, 2, 31, 128, 129],
+    [2, 2, 2, 3, 2, 4, 2, 2, 3, 2, 2, 5],
+], ids=["mixed", "mode-boundaries", "tiny-shared-tiles"])
+def test_train_step_vs_fp64_oracle_ragged(golden, dev, n_list):
     """A ragged synthetic group (N = 2 .. 130, spanning several TXP-CNN tiles and the NJ = 1..8
     kernel variants) against the oracle evaluated in fp64 on the same inputs."""
     import social_stgcnn_b200 as sstg
     from social_stgcnn_b200 import engine as E
     from oracle import stgcnn_oracle as O
-    n_list = [2, 3, 33, 64, 7, 130, 5, 40]
     obs_rel, pred_rel, _ = O.synthetic_scenes(1, sum(n_list), seed=77)
     params, bn = golden.params("zara1")
     eng = sstg.TrainEngine(params, bn, dev)
     plan = sstg.ScenePlan(n_list)
-    bs = 8
+    bs = len(n_list)
     r = eng.forward_backward(plan, torch.from_numpy(obs_rel).to(dev), torch.from_numpy(pred_rel).to(dev),
                              E.group_weights(len(n_list), bs))
     E.bn_running_update(plan.on(dev), r["scene_stats"], eng.bn)
