@@ -350,6 +350,36 @@ def run_train_leg(dev, world, rank, steps, warmup, batch=128):
         nccl = {"value": batch * steps / (ms_nccl * 1e-3), "unit": "scenes/s", "ms_per_group": ms_nccl / steps,
                 "what": "same sharded group, exchange through one torch.distributed (NCCL) all-reduce instead"}
     peds = float(np.mean([g[0].sum() for g in groups]))
+    # the same loop through the public driver (driver.train_epoch: shuffled epoch order, per-epoch gather and
+    # plan upload, one library call per group), wall clock, on an ETH-train-sized synthetic split
+    epoch = None
+    if world == 1:
+        import time
+        from social_stgcnn_b200 import driver
+        S_ep = 2816
+        n_ep = synth_ragged_counts(S_ep, 5)
+        o_ep, p_ep, _ = synth_batch(int(n_ep.sum()), 1, 9)
+
+        class _Split:
+            packed = {"device": dev, "obs_rel": o_ep.to(dev), "pred_rel": p_ep.to(dev)}
+            plan_obs = sstg.ScenePlan(n_ep)
+
+            def __len__(self):
+                return S_ep
+
+        eng_ep = sstg.TrainEngine(params, bn, dev)
+        rng = np.random.default_rng(0)
+        driver.train_epoch(_Split(), eng_ep, batch, 1e-4, order=rng.permutation(S_ep))
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        n_epochs = 5
+        for _ in range(n_epochs):
+            driver.train_epoch(_Split(), eng_ep, batch, 1e-4, order=rng.permutation(S_ep))
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / n_epochs
+        epoch = {"value": S_ep / dt, "unit": "scenes/s", "ms_per_epoch": dt * 1e3, "scenes": S_ep,
+                 "what": "driver.train_epoch (the train() replacement) on 2,816 ragged scenes, shuffled order, "
+                         "wall clock incl. the per-epoch host preparation"}
     indep = None
     if world > 1:
         # the reference's own multi-GPU recipe (train.sh:4-18): independent trainings side by side, one per GPU,
@@ -371,7 +401,7 @@ def run_train_leg(dev, world, rank, steps, warmup, batch=128):
         indep = {"value": world * batch * steps / (float(t2[0]) * 1e-3), "unit": "scenes/s",
                  "what": "independent trainings, one per GPU, as the reference's train.sh launches them (no collective)"}
     return {"value": batch * steps / (ms * 1e-3), "unit": "scenes/s", "ms_per_group": ms / steps, "batch": batch,
-            "exchange": exchange, "nccl_exchange": nccl, "independent_replicas": indep,
+            "exchange": exchange, "nccl_exchange": nccl, "independent_replicas": indep, "epoch_through_driver": epoch,
             "groups_timed": steps, "mean_peds_per_group": peds, "n_gpus": world,
             "what": "train(): graph build + train-mode fwd (per-scene BN stats) + NLL + full bwd + BN running stats "
                     "+ SGD, one packed ragged group of 128 ETH/UCY-shaped scenes per step (8 distinct groups cycled; a "

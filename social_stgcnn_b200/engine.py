@@ -109,6 +109,38 @@ class DevicePlan:
     tile_off: torch.Tensor
 
 
+def plan_groups(n_peds_list, device, T: int = L.T_OBS):
+    """ScenePlans of many batches (e.g. all optimiser groups of an epoch) whose offset tables reach the
+    device in ONE host->device copy instead of one per plan.  Returns the list of ScenePlans with
+    `.on(device)` already resolved."""
+    device = torch.device(device)
+    if device.type != "cuda":
+        raise RuntimeError("plan_groups(): a CUDA device is required (no CPU fallback)")
+    if device.index is None:
+        device = torch.device("cuda", torch.cuda.current_device())
+    plans = [ScenePlan(n, T) for n in n_peds_list]
+    up16 = lambda x: (x + 15) & ~15
+    offs, total = [], 0
+    for p in plans:
+        o_a = total
+        o_s = o_a + up16(p.a_off.nbytes)
+        o_t = o_s + up16(p.seg_off.nbytes)
+        total = o_t + up16(p.tile_off.nbytes)
+        offs.append((o_a, o_s, o_t))
+    host = np.zeros(max(total, 16), np.uint8)
+    for p, (o_a, o_s, o_t) in zip(plans, offs):
+        host[o_a:o_a + p.a_off.nbytes] = p.a_off.view(np.uint8)
+        host[o_s:o_s + p.seg_off.nbytes] = p.seg_off.view(np.uint8)
+        host[o_t:o_t + p.tile_off.nbytes] = p.tile_off.view(np.uint8)
+    buf = torch.from_numpy(host).to(device)
+    for p, (o_a, o_s, o_t) in zip(plans, offs):
+        p._dev[device] = DevicePlan(p, device,
+                                    buf[o_s:o_s + p.seg_off.nbytes].view(torch.int32),
+                                    buf[o_a:o_a + p.a_off.nbytes].view(torch.int64),
+                                    buf[o_t:o_t + p.tile_off.nbytes].view(torch.int32))
+    return plans
+
+
 # --------------------------------------------------------------------------
 # functional ops (device tensors in, device tensors out; `out=` to reuse buffers)
 # --------------------------------------------------------------------------
