@@ -66,6 +66,18 @@ def evaluate(dataset, engine: E.InferenceEngine, KSTEPS: int = 20, seed: int = 0
     return ade_, fde_, raw
 
 
+def epoch_rows(seg_off, n_peds, order):
+    """Pedestrian rows of the packed dataset in epoch order, and each scene's [start, end) inside that
+    gathered order: after ONE index_select with `rows`, every optimiser group is a contiguous slice."""
+    order = np.asarray(order, np.int64)
+    counts = np.asarray(n_peds, np.int64)[order]
+    ped_end = np.cumsum(counts)
+    ped_start = ped_end - counts
+    total = int(ped_end[-1]) if order.size else 0
+    rows = np.repeat(np.asarray(seg_off, np.int64)[order] - ped_start, counts) + np.arange(total, dtype=np.int64)
+    return rows, ped_start, ped_end
+
+
 def train_epoch(dataset, engine: E.TrainEngine, batch_size: int = 128, lr: float = 0.01,
                 clip_grad: Optional[float] = None, order=None, trainer=None):
     """train() of the reference (train.py:28-79) over one epoch.
@@ -87,10 +99,7 @@ def train_epoch(dataset, engine: E.TrainEngine, batch_size: int = 128, lr: float
     # ---- the epoch is prepared in one pass (the per-group device time is ~0.13 ms, so anything done per
     # group on the host decides the epoch time): ONE gather of the pedestrian rows in epoch order -- every
     # group is then a contiguous slice -- and ONE upload of all the groups' offset tables
-    counts = n_all[order].astype(np.int64)
-    ped_end = np.cumsum(counts)
-    ped_start = ped_end - counts
-    rows = np.repeat(seg[order] - ped_start, counts) + np.arange(int(ped_end[-1]), dtype=np.int64)
+    rows, ped_start, ped_end = epoch_rows(seg, n_all, order)
     rows_d = torch.from_numpy(rows).to(dev)
     obs_e, pred_e = pk["obs_rel"].index_select(0, rows_d), pk["pred_rel"].index_select(0, rows_d)
     bounds = list(range(0, S, batch_size)) + [S]

@@ -127,3 +127,21 @@ def test_pack_tracks_format_and_overflow(golden):
         sstg.pack_tracks(bad)
     with pytest.raises(ValueError):
         sstg.pack_tracks(traj[:, :, :8])
+
+
+def test_epoch_rows_is_the_per_scene_concatenation():
+    """driver.epoch_rows (one gather per epoch) == concatenating every scene's pedestrian rows in epoch order."""
+    from social_stgcnn_b200.driver import epoch_rows
+    rng = np.random.default_rng(3)
+    n = rng.integers(2, 58, 300)
+    seg = np.concatenate([[0], np.cumsum(n)])
+    order = rng.permutation(300)
+    rows, start, end = epoch_rows(seg, n, order)
+    ref = np.concatenate([np.arange(seg[s], seg[s + 1]) for s in order])
+    assert np.array_equal(rows, ref)
+    assert np.array_equal(end - start, n[order]) and start[0] == 0 and end[-1] == n.sum()
+    # a group of scenes order[a:b] is the contiguous slice [start[a], end[b-1])
+    a, b = 128, 256
+    assert np.array_equal(rows[start[a]:end[b - 1]], np.concatenate([np.arange(seg[s], seg[s + 1]) for s in order[a:b]]))
+    rows0, s0, e0 = epoch_rows(seg, n, np.zeros(0, np.int64))
+    assert rows0.size == 0 and s0.size == 0
