@@ -60,16 +60,28 @@ class ScenePlan:
         self._dev: Dict[torch.device, "DevicePlan"] = {}
         self._cache: Dict[tuple, list] = {}
 
-    def chunks(self, chunk_scenes: int):
+    def chunks(self, chunk_scenes: int, taper: bool = False):
         """Contiguous sub-plans of at most `chunk_scenes` scenes: [(scene lo, hi, ped lo, hi, ScenePlan)].
-        Identical pedestrian-count patterns share one sub-plan (and its device offsets)."""
+        Identical pedestrian-count patterns share one sub-plan (and its device offsets).
+        `taper`: a quarter-size first and last chunk -- in a copy/compute pipeline the first chunk's copy and
+        the last chunk's kernels are the parts nothing overlaps, so they are kept short."""
         chunk_scenes = max(1, int(chunk_scenes))
-        key = ("chunks", chunk_scenes)
+        key = ("chunks", chunk_scenes, bool(taper))
         got = self._cache.get(key)
         if got is None:
+            q = chunk_scenes // 4
+            if taper and q >= 1 and self.S > 2 * chunk_scenes:
+                mid = self.S - 2 * q
+                cuts = [0, q] + [q + k * chunk_scenes for k in range(1, mid // chunk_scenes + 1)]
+                if mid % chunk_scenes:
+                    cuts.append(self.S - q)
+                cuts.append(self.S)
+            else:
+                cuts = list(range(0, self.S, chunk_scenes)) + [self.S]
             got, uniq = [], {}
-            for lo in range(0, self.S, chunk_scenes):
-                hi = min(self.S, lo + chunk_scenes)
+            for lo, hi in zip(cuts[:-1], cuts[1:]):
+                if hi <= lo:
+                    continue
                 n = self.n_peds[lo:hi]
                 sub = uniq.get(n.tobytes())
                 if sub is None:
@@ -386,12 +398,13 @@ class InferenceEngine:
         return out
 
     def infer_host(self, plan: ScenePlan, obs_rel, pred_rel, last_obs, K: int = 20, *, chunk_scenes: int = 8192,
-                   seed: int = 0, compact=None, fused: bool = True, **kw):
+                   seed: int = 0, compact=None, fused: bool = True, taper: bool = True, **kw):
         """End-to-end call with HOST buffers (numpy or CPU tensors, ideally pinned): the batch is
         cut into chunks of `chunk_scenes` scenes and software-pipelined over three streams --
         H2D of chunk i+1 (copy stream) overlaps the kernels of chunk i (current stream) and the
         D2H of chunk i-1's per-pedestrian minima (second copy stream).  PCIe carries 168 B per
-        pedestrian in and 16 B out, so the steady state is max(H2D time, kernel time).
+        pedestrian in and 16 B out, so the steady state is max(H2D time, kernel time); the first and the
+        last chunk are a quarter of the size (`taper`), which shortens the pipeline's fill and drain.
         Only the per-pedestrian minima leave the device, so by default (`fused`) graph build and
         st_gcn run as the fused pair that keeps the adjacency on chip (scenes of <= 64 pedestrians).
         `compact=(start, delta)` (pack_tracks) replaces the three fp32 host tensors by the 88 B per
@@ -403,7 +416,7 @@ class InferenceEngine:
                                            torch.as_tensor(last_obs))
         else:
             c_start, c_delta = torch.as_tensor(compact[0]), torch.as_tensor(compact[1])
-        chunks = plan.chunks(chunk_scenes)
+        chunks = plan.chunks(chunk_scenes, taper)
         key = (plan.P, max(c[4].P for c in chunks))
         st = self._pin.get(key)
         if st is None:

@@ -266,7 +266,7 @@ def test_infer_host_pipelined_chunks_equal_direct_calls(golden, batch, dev):
     for chunk, fused in ((7, True), (32, False), (10 ** 6, True)):
         a_h, f_h = eng.infer_host(plan, obs_h, pred_h, last_h, 20, chunk_scenes=chunk, seed=5, fused=fused)
         a_h, f_h = a_h.copy(), f_h.copy()
-        for i, (lo, hi, p_lo, p_hi, sub) in enumerate(plan.chunks(chunk)):
+        for i, (lo, hi, p_lo, p_hi, sub) in enumerate(plan.chunks(chunk, taper=True)):
             r = eng.infer(sub, batch["obs_rel"][p_lo:p_hi].contiguous(), batch["pred_rel"][p_lo:p_hi].contiguous(),
                           batch["last_obs"][p_lo:p_hi].contiguous(), 20, seed=5 + 0x9E3779B1 * i, fused=fused)
             torch.cuda.synchronize()

@@ -145,3 +145,20 @@ def test_epoch_rows_is_the_per_scene_concatenation():
     assert np.array_equal(rows[start[a]:end[b - 1]], np.concatenate([np.arange(seg[s], seg[s + 1]) for s in order[a:b]]))
     rows0, s0, e0 = epoch_rows(seg, n, np.zeros(0, np.int64))
     assert rows0.size == 0 and s0.size == 0
+
+
+def test_chunk_schedules_cover_the_batch_once():
+    """ScenePlan.chunks: uniform and tapered (quarter-size first / last chunk) schedules are contiguous
+    partitions of the scenes, and identical pedestrian-count patterns share one sub-plan."""
+    import social_stgcnn_b200 as sstg
+    plan = sstg.ScenePlan(np.full(1000, 4, np.int32))
+    for chunk, taper in ((64, False), (64, True), (7, True), (3, True), (5000, True), (300, True)):
+        ch = plan.chunks(chunk, taper)
+        assert ch[0][0] == 0 and ch[-1][1] == plan.S
+        assert all(a[1] == b[0] and a[3] == b[2] for a, b in zip(ch[:-1], ch[1:]))
+        assert all(0 < hi - lo <= chunk and sub.S == hi - lo for lo, hi, _, _, sub in ch)
+    ch = plan.chunks(64, True)
+    assert ch[0][1] - ch[0][0] == 16 and ch[-1][1] - ch[-1][0] == 16          # quarter-size ends
+    assert len({id(c[4]) for c in ch}) <= 3                                    # head/tail, full, remainder
+    assert len(plan.chunks(7)) == (1000 + 6) // 7
+    assert sstg.ScenePlan([]).chunks(8, True) == []
