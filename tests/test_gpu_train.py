@@ -246,4 +246,57 @@ def test_fused_step_call_equals_separate_calls(golden, dev):
         torch.cuda.synchronize()
         assert torch.equal(a.params, b.params) and torch.equal(a.bn, b.bn), it
         assert abs(float(la) - float(lb)) < 1e-6 * max(1.0, abs(float(lb)))
-    assert a.num_batches_tracked == b.num_batches_tracked == 36
+    for it in range(2):                              # no clipping: SGD is applied inside the tail kernel
+        la = a.step(plan, o, p, batch_size=12, lr=0.01)
+        lb = b.step_unfused(plan, o, p, batch_size=12, lr=0.01, graph_fp64=False)
+        torch.cuda.synchronize()
+        assert torch.equal(a.params, b.params) and torch.equal(a.bn, b.bn), it
+        assert torch.equal(a.grad, b.grad)
+    assert a.num_batches_tracked == b.num_batches_tracked == 60
+
+
+def test_train_step_stays_inside_its_buffers(golden, dev):
+    """compute-sanitizer is not available on this pool, so the one-call training step is run with every
+    buffer it writes (workspace of exactly sstg_train_step_workspace floats, loss, grad) embedded in a
+    sentinel-filled arena: all sentinels must survive, for tile shapes that hit every small-tile form."""
+    import ctypes
+    import social_stgcnn_b200 as sstg
+    from social_stgcnn_b200 import _lib as L
+    from social_stgcnn_b200 import engine as E
+    from oracle import stgcnn_oracle as O
+    lib = L.load()
+    params, bn = golden.params("eth")
+    SENT = 0x7fc0dead                                      # a NaN bit pattern no kernel produces
+    for n_list in ([2, 2, 3, 2, 5, 2], [32, 33, 64, 65, 2, 31], [128, 129, 7], [57] * 5):
+        plan = sstg.ScenePlan(n_list)
+        dp = plan.on(dev)
+        obs_rel, pred_rel, _ = O.synthetic_scenes(1, sum(n_list), seed=3)
+        o, p = torch.from_numpy(obs_rel).to(dev), torch.from_numpy(pred_rel).to(dev)
+        need = int(lib.sstg_train_step_workspace(plan.S, plan.n_tiles, plan.P, plan.a_floats))
+        G = 4096                                           # guard floats on every side
+        sizes = [need, plan.S + 1, L.N_PARAMS]             # ws | loss (+ group loss) | grad
+        arena = torch.full((sum(sizes) + G * (len(sizes) + 1),), 0, dtype=torch.int32, device=dev)
+        arena.fill_(SENT)
+        offs, cur = [], G
+        for sz in sizes:
+            offs.append(cur)
+            cur += sz + G
+        fl = arena.view(torch.float32)
+        ws, loss, grad = (fl[o_:o_ + sz] for o_, sz in zip(offs, sizes))
+        assert ws.data_ptr() % 16 == 0
+        prm = torch.from_numpy(params.astype(np.float32)).to(dev)
+        bnb = torch.from_numpy(bn.astype(np.float32)).to(dev)
+        w = torch.from_numpy(E.group_weights(plan.S, plan.S)).to(dev)
+        rc = lib.sstg_train_step(o.data_ptr(), p.data_ptr(), dp.seg_off.data_ptr(), dp.a_off.data_ptr(),
+                                 dp.tile_off.data_ptr(), plan.S, plan.n_tiles, plan.max_n, plan.P, plan.a_floats,
+                                 prm.data_ptr(), bnb.data_ptr(), w.data_ptr(), ws.data_ptr(), need, 0.01, 0.0, 0.1, 0,
+                                 loss.data_ptr(), grad.data_ptr(), loss.data_ptr() + 4 * plan.S,
+                                 torch.cuda.current_stream(dev).cuda_stream)
+        assert rc == 0
+        torch.cuda.synchronize()
+        mask = torch.ones_like(arena, dtype=torch.bool)
+        for o_, sz in zip(offs, sizes):
+            mask[o_:o_ + sz] = False
+        assert bool((arena[mask] == SENT).all()), n_list     # nothing outside the three buffers was touched
+        assert bool(torch.isfinite(grad).all()) and bool(torch.isfinite(loss).all())
+        assert prm.numel() == L.N_PARAMS and bool(torch.isfinite(prm).all())
