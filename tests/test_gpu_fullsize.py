@@ -8,6 +8,8 @@ oracle cannot run everything: size-independent properties plus oracle spot check
   * dense crowds (32,768 scenes x 64): Laplacian identities (symmetry, D^1/2 in the null space),
     finiteness, min-over-K monotonicity (the k-th Philox sample does not depend on K), chunked
     host pipeline == one-shot pipeline, and oracle spot checks on random scenes."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -196,3 +198,49 @@ def test_large_scenes_256_pedestrians(golden, dev):
     assert abs(got_loss - lo) < 1e-5 * max(1.0, abs(lo))
     g = r["grad"].cpu().numpy().astype(np.float64)
     assert np.abs(g - go).max() < 5e-5 * np.abs(go).max()
+
+
+def test_inference_kernels_stay_inside_their_buffers(golden, dev):
+    """compute-sanitizer is not available on this pool: every output buffer of the inference kernels
+    (V, A, H, the fused front's scratch, V_pred, the per-pedestrian minima) is carved out of a sentinel-filled
+    arena with guard bands; after graph build, st_gcn (plain and fused), TXP-CNN (Winograd and direct) and
+    sampling, every sentinel must be intact -- ragged, tile-boundary and 256-pedestrian shapes."""
+    import social_stgcnn_b200 as sstg
+    from oracle import stgcnn_oracle as O
+    params, bn = golden.params("eth")
+    prm, bnb = torch.from_numpy(params).to(dev), torch.from_numpy(bn).to(dev)
+    SENT = 0x7fc0dead
+    G = 4096
+    for n_list in ([2, 3, 2, 57, 5, 2, 31, 33], [64] * 40, [127, 128, 129, 2], [256, 3, 255], [2] * 300):
+        plan = sstg.ScenePlan(n_list)
+        dp = plan.on(dev)
+        P = plan.P
+        obs_rel, pred_rel, obs_abs = O.synthetic_scenes(1, P, seed=11)
+        o, p, l = (torch.from_numpy(np.ascontiguousarray(x)).to(dev) for x in (obs_rel, pred_rel, obs_abs[:, :, -1]))
+        sizes = {"V": P * 16, "A": plan.a_floats, "H": P * 40, "H2": P * 40, "Pws": P * 40, "out": P * 60,
+                 "out2": P * 60, "ade": 2 * P, "fde": 2 * P}                       # fp64 minima: 2 floats each
+        sizes = {k: (v + 3) & ~3 for k, v in sizes.items()}
+        arena = torch.empty(sum(sizes.values()) + G * (len(sizes) + 1), dtype=torch.int32, device=dev)
+        arena.fill_(SENT)
+        fl, buf, cur = arena.view(torch.float32), {}, G
+        mask = torch.ones_like(arena, dtype=torch.bool)
+        for k, sz in sizes.items():
+            buf[k] = fl[cur:cur + sz]
+            mask[cur:cur + sz] = False
+            cur += sz + G
+        V, A = sstg.graph_build(dp, o, 8, V=buf["V"][:P * 16], A=buf["A"][:plan.a_floats])
+        H = sstg.stgcn_forward(dp, V, A, prm, bnb, H=buf["H"][:P * 40])
+        if plan.max_n <= 64:
+            sstg.stgcn_forward_fused(dp, o, prm, bnb, H=buf["H2"][:P * 40], Pws=buf["Pws"][:P * 40])
+        out = sstg.txpcnn_forward(dp, H, prm, out=buf["out"][:P * 60])
+        os.environ["SSTG_TXP_WINO"] = "0"                                          # the direct FFMA2 kernel as well
+        try:
+            sstg.txpcnn_forward(dp, H, prm, out=buf["out2"][:P * 60])
+        finally:
+            os.environ.pop("SSTG_TXP_WINO", None)
+        sstg.sample_ade_fde(dp, out, p, l, 20, seed=1, fp64_dist=False, vtr_is_rel=True,
+                            min_ade=buf["ade"][:2 * P].view(torch.float64), min_fde=buf["fde"][:2 * P].view(torch.float64))
+        torch.cuda.synchronize()
+        assert bool((arena[mask] == SENT).all()), n_list
+        assert bool(torch.isfinite(buf["out"][:P * 60]).all()) and bool(torch.isfinite(buf["ade"][:2 * P].view(torch.float64)).all())
+        assert float((buf["out"][:P * 60] - buf["out2"][:P * 60]).abs().max()) < 1e-4
