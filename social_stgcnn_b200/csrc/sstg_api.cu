@@ -318,13 +318,22 @@ int sstg_train_step(const float* obs_rel, const float* pred_rel, const int32_t* 
   const int gf = SSTG_GRAPH_NORM_LAP | (graph_flags & SSTG_GRAPH_FP64);
   int rc = sstg_graph_build(obs_rel, seg_off, a_off, S, SSTG_T_OBS, max_n, ws + w.V, ws + w.A, gf, stream);
   if (rc) return rc;
-  rc = sstg_graph_build(pred_rel, seg_off, nullptr, S, SSTG_T_PRED, max_n, ws + w.Vtr, nullptr, SSTG_GRAPH_V_ONLY, stream);
-  if (rc) return rc;
-  rc = sstg_forward_train(ws + w.V, ws + w.A, seg_off, a_off, tile_off, S, n_tiles, max_n, total_peds, params,
-                          ws + w.save, ws + w.stats, ws + w.vp, stream);
-  if (rc) return rc;
-  rc = sstg_nll_backward(ws + w.vp, ws + w.Vtr, seg_off, S, scene_weight, loss, ws + w.dvp, stream);
-  if (rc) return rc;
+  // (no V_tr pass: the NLL kernel reads the targets straight out of pred_traj_rel)
+  {
+    // forward: the BatchNorm running-statistics recurrence rides along as an extra CTA of the TXP-CNN launch
+    const long long P = total_peds;
+    float* save = ws + w.save;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    rc = launch_stgcn_train_forward(ws + w.V, ws + w.A, seg_off, a_off, S, max_n, params, save, save + P * 40,
+                                    save + P * 80, ws + w.stats, st);
+    if (rc) return rc;
+    rc = launch_txpcnn_forward(save + P * 80, seg_off, tile_off, n_tiles, max_n, params, ws + w.vp, save + P * 120,
+                               save + P * 360, P * 60, 0, st, ws + w.stats, S, bn_momentum,
+                               bn_momentum >= 0.0 ? bn : nullptr);
+    if (rc) return rc;
+    rc = launch_nll_fwd_bwd(ws + w.vp, pred_rel, seg_off, S, scene_weight, loss, ws + w.dvp, st, /*vtr_is_rel=*/1);
+    if (rc) return rc;
+  }
   // backward without its own gradient reduction: the reduction, the BN recurrence, the group loss and
   // (without clipping) the SGD update share ONE launch
   {
@@ -339,8 +348,8 @@ int sstg_train_step(const float* obs_rel, const float* pred_rel, const int32_t* 
     if (rc) return rc;
     const bool clip = clip_norm > 0.f;
     rc = launch_train_tail(ws + w.pst, stgcn_train_bwd_rows(S), ws + w.ptx, txpcnn_bwd_rows(n_tiles),
-                           SSTG_TXP_GRAD_STRIDE, grad, params, clip ? 0.f : lr, ws + w.stats, seg_off, S, bn_momentum,
-                           bn, loss, scene_weight, group_loss, st);
+                           SSTG_TXP_GRAD_STRIDE, grad, params, clip ? 0.f : lr, ws + w.stats, seg_off, S,
+                           /*BN recurrence already done=*/-1.0, bn, loss, scene_weight, group_loss, st);
     if (rc) return rc;
     if (clip && lr != 0.f) rc = sstg_sgd_step(params, grad, SSTG_N_PARAMS, lr, clip_norm, nullptr, stream);
   }

@@ -142,7 +142,8 @@ int launch_stgcn_forward(const float* V, const float* A, const int32_t* seg_off,
                          cudaStream_t st);
 int launch_txpcnn_forward(const float* H, const int32_t* seg_off, const int32_t* tile_off, int n_tiles, int max_n,
                           const float* params, float* out, float* Usave, float* Xsave, long long layer_stride,
-                          int tile_cols, cudaStream_t st);
+                          int tile_cols, cudaStream_t st, const float* bn_stats = nullptr, int bn_scenes = 0,
+                          double bn_momentum = 0.0, float* bn = nullptr);
 int launch_rel_to_abs(const float* rel, const double* init, const int32_t* seg_off, int S, int P, int T, float* out,
                       cudaStream_t st);
 int launch_traj_error(const float* pred, const float* tgt, const int32_t* seg_off, int S, int P, int T,
@@ -167,7 +168,7 @@ int launch_stgcn_train_backward(const float* V, const float* A, const int32_t* s
                                 int max_n, const float* params, const float* Y, const float* Z,
                                 const float* stats, const float* dH, float* partial, cudaStream_t st);
 int launch_nll_fwd_bwd(const float* Vpred, const float* Vtr, const int32_t* seg_off, int S, const float* weight,
-                       float* loss, float* dV, cudaStream_t st);
+                       float* loss, float* dV, cudaStream_t st, int vtr_is_rel = 0);
 int launch_bn_running_update(const float* stats, const int32_t* seg_off, int S, double momentum, float* bn,
                              cudaStream_t st, const int32_t* abort_flag = nullptr);
 int preload_bn_running_update();

@@ -18,6 +18,7 @@
 // per-CTA partial row; sstg_grad_finalize sums the rows in ascending CTA order, so the
 // result is bit-reproducible for a given grid (no float atomics anywhere).
 #include "sstg_common.cuh"
+#include "bn_update.cuh"
 
 namespace sstg {
 
@@ -609,7 +610,7 @@ constexpr int NLL_THREADS = T_PRED * 32;
 __global__ void __launch_bounds__(NLL_THREADS)
 nll_fwd_bwd_kernel(const float* __restrict__ Vpred, const float* __restrict__ Vtr,
                    const int32_t* __restrict__ seg_off, int S, const float* __restrict__ weight,
-                   float* __restrict__ loss, float* __restrict__ dV) {
+                   float* __restrict__ loss, float* __restrict__ dV, int vtr_is_rel) {
   __shared__ float part[T_PRED];
   const int t = threadIdx.x >> 5, lane = threadIdx.x & 31;
   pdl_wait();
@@ -624,7 +625,13 @@ nll_fwd_bwd_kernel(const float* __restrict__ Vpred, const float* __restrict__ Vt
     float sum = 0.f;
     for (int n = lane; n < N; n += 32) {
       const int i = t * N + n;
-      const float2 tr = vt[i];
+      float2 tr;
+      if (vtr_is_rel) {  // Vtr is pred_traj_rel [P,2,12] itself: the target V_tr (utils.py:44) is its transpose
+        const float* pr = Vtr + static_cast<size_t>(n0 + n) * (2 * T_PRED) + t;
+        tr = make_float2(__ldg(pr), __ldg(pr + T_PRED));
+      } else {
+        tr = vt[i];
+      }
       const float m0 = vp[i], m1 = vp[12 * N + i], l2 = vp[24 * N + i], l3 = vp[36 * N + i], l4 = vp[48 * N + i];
       const float nx = tr.x - m0;
       const float ny = tr.y - m1;
@@ -671,42 +678,7 @@ nll_fwd_bwd_kernel(const float* __restrict__ Vpred, const float* __restrict__ Vt
 // BatchNorm running statistics: r <- (1 - m) r + m s_i, scene after scene, unbiased var.
 // 30 threads; ATen's CPU kernel evaluates the update in double, so do we.
 // ---------------------------------------------------------------------------------------
-constexpr int BN_TILE = 128;  // scenes staged per pass (128 x 30 doubles = 30 KB of static shared memory)
-__device__ __forceinline__ void bn_running_update_body(const float* __restrict__ stats,
-                                                       const int32_t* __restrict__ seg_off, int S, double momentum,
-                                                       float* __restrict__ bn) {
-  // The recurrence is sequential in the scene index, but its inputs are not: 256 threads stage a
-  // tile of per-scene statistics (and element counts) in shared memory with coalesced loads, then
-  // 30 threads run the recurrence over the tile out of shared memory.
-  __shared__ double st[BN_TILE * SSTG_N_BN];  // momentum * (mean | unbiased variance), ready for the recurrence
-  __shared__ double fac[BN_TILE];             // momentum * M / (M - 1) of each staged scene
-  const int i = threadIdx.x;
-  double r = i < SSTG_N_BN ? static_cast<double>(bn[i]) : 0.0;
-  for (int s0 = 0; s0 < S; s0 += BN_TILE) {
-    const int ns = (S - s0 < BN_TILE) ? (S - s0) : BN_TILE;
-    // the unbiased-variance factor M / (M - 1): ONE fp64 division per scene, by one thread per scene (the
-    // division is the expensive part; it is neither inside the sequential recurrence nor repeated per channel)
-    if (i < ns) {
-      const double M = static_cast<double>(T_OBS) * (seg_off[s0 + i + 1] - seg_off[s0 + i]);
-      fac[i] = momentum * (M / (M - 1.0));
-    }
-    __syncthreads();
-    for (int j = threadIdx.x; j < ns * SSTG_N_BN; j += blockDim.x) {
-      const int s = j / SSTG_N_BN, k = j - s * SSTG_N_BN;
-      const double v = stats[static_cast<size_t>(s0) * SSTG_N_BN + j];
-      st[j] = ((k / 5) & 1) ? fac[s] * v : momentum * v;
-    }
-    __syncthreads();
-    if (i < SSTG_N_BN) {
-      const double keep = 1.0 - momentum;
-      for (int s = 0; s < ns; ++s)
-        r = static_cast<double>(static_cast<float>(st[s * SSTG_N_BN + i] + keep * r));
-    }
-    __syncthreads();
-  }
-  if (i < SSTG_N_BN) bn[i] = static_cast<float>(r);
-}
-
+// (the recurrence itself lives in bn_update.cuh: the TXP-CNN training forward runs it as an extra CTA)
 __global__ void __launch_bounds__(256)
 bn_running_update_kernel(const float* __restrict__ stats, const int32_t* __restrict__ seg_off, int S,
                          double momentum, float* __restrict__ bn, const int32_t* __restrict__ abort_flag) {
@@ -887,11 +859,11 @@ int launch_stgcn_train_backward(const float* V, const float* A, const int32_t* s
 }
 
 int launch_nll_fwd_bwd(const float* Vpred, const float* Vtr, const int32_t* seg_off, int S, const float* weight,
-                       float* loss, float* dV, cudaStream_t st) {
+                       float* loss, float* dV, cudaStream_t st, int vtr_is_rel) {
   if (S == 0) return SSTG_OK;
   const int cap = 8 * 148;
   SSTG_CUDA_TRY(launch_pdl(nll_fwd_bwd_kernel, S < cap ? S : cap, NLL_THREADS, 0, st, Vpred, Vtr, seg_off, S, weight,
-                           loss, dV),
+                           loss, dV, vtr_is_rel),
                 "nll_fwd_bwd launch");
   return SSTG_OK;
 }

@@ -29,6 +29,7 @@
 // this direct kernel serves training (SAVE: it also stores every layer's pre-activation and
 // output for the backward pass) and larger scenes.
 #include "txpcnn_common.cuh"
+#include "bn_update.cuh"
 
 namespace sstg {
 
@@ -42,7 +43,7 @@ using namespace txp;
 __device__ long long g_phase_xf[160 * 16];
 #define PHASE_XF(k)                                                                                      \
   do {                                                                                                   \
-    if (threadIdx.x == 0 && tile == static_cast<int>(blockIdx.x)) g_phase_xf[blockIdx.x * 16 + (k)] = clock64(); \
+    if (threadIdx.x == 0 && tile == cta) g_phase_xf[cta * 16 + (k)] = clock64(); \
   } while (0)
 #else
 #define PHASE_XF(k)
@@ -56,7 +57,22 @@ __global__ void __launch_bounds__(X_THREADS)
 txpcnn_fwd_kernel(const float* __restrict__ Hin, const int32_t* __restrict__ seg_off,
                   const int32_t* __restrict__ tile_off, int n_tiles, int Wp, const float* __restrict__ params,
                   float* __restrict__ out, float* __restrict__ Usave, float* __restrict__ Xsave,
-                  long long layer_stride) {
+                  long long layer_stride, const float* __restrict__ bn_stats, int bn_scenes, double bn_momentum,
+                  float* __restrict__ bn) {
+  // Training only: when `bn` is given, CTA 0 of the grid is not a convolution CTA -- it runs the BatchNorm
+  // running-statistics recurrence (sequential over the scenes, ~10 us for a 128-scene group) underneath the
+  // convolutions instead of on the critical path at the end of the step.
+  const int bn_ctas = (SAVE && bn != nullptr) ? 1 : 0;
+  const int conv_ctas = static_cast<int>(gridDim.x) - bn_ctas;
+  const int cta = static_cast<int>(blockIdx.x) - bn_ctas;   // index among the convolution CTAs
+  if constexpr (SAVE) {
+    if (bn != nullptr && blockIdx.x == 0) {
+      pdl_wait();  // the statistics come from the st_gcn forward
+      pdl_release();
+      bn_running_update_body(bn_stats, seg_off, bn_scenes, bn_momentum, bn);
+      return;
+    }
+  }
   extern __shared__ __align__(16) unsigned char smem_raw[];
   XSmem& sm = *reinterpret_cast<XSmem*>(smem_raw);
   float* act = reinterpret_cast<float*>(smem_raw + ((sizeof(XSmem) + 15) & ~size_t(15)));  // [60][Wp]
@@ -64,7 +80,7 @@ txpcnn_fwd_kernel(const float* __restrict__ Hin, const int32_t* __restrict__ seg
   const int half = tid / X_COLS;  // warp-uniform
   const int idx = tid - half * X_COLS;
 #ifdef SSTG_PHASE_CLOCKS
-  if (tid == 0) g_phase_xf[blockIdx.x * 16 + 0] = clock64();
+  if (tid == 0 && cta < 160) g_phase_xf[cta * 16 + 0] = clock64();
 #endif
 
   // ---- weights: params [co][ci][3][3] -> shared [layer][ci][half][tap][co%6]  (tap-major for FFMA2 pairs);
@@ -110,7 +126,7 @@ txpcnn_fwd_kernel(const float* __restrict__ Hin, const int32_t* __restrict__ seg
   pdl_wait();  // everything above read only `params`
   pdl_release();
 
-  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+  for (int tile = cta; tile < n_tiles; tile += conv_ctas) {
     PHASE_XF(1);
     const int s_lo = tile_off[tile], s_hi = tile_off[tile + 1];
     const int p_lo = seg_off[s_lo];
@@ -283,7 +299,8 @@ int txpcnn_tile_width(int max_n) {
 
 int launch_txpcnn_forward(const float* H, const int32_t* seg_off, const int32_t* tile_off, int n_tiles, int max_n,
                           const float* params, float* out, float* Usave, float* Xsave, long long layer_stride,
-                          int tile_cols, cudaStream_t st) {
+                          int tile_cols, cudaStream_t st, const float* bn_stats, int bn_scenes, double bn_momentum,
+                          float* bn) {
   if (n_tiles == 0) return SSTG_OK;
   const bool save = Usave != nullptr && Xsave != nullptr;
   // inference on scenes of up to 128 pedestrians: the Winograd F(2,3) kernel (txpcnn_wino.cu)
@@ -307,12 +324,15 @@ int launch_txpcnn_forward(const float* H, const int32_t* seg_off, const int32_t*
     const long long want = static_cast<long long>(sms) * per_sm;
     const int grid = static_cast<int>(n_tiles < want ? n_tiles : want);
     if (save) {
-      SSTG_CUDA_TRY(launch_pdl(kern, grid, X_THREADS, smem, st, H, seg_off, tile_off, n_tiles, Wp, params, out, Usave,
-                               Xsave, layer_stride),
+      const bool with_bn = bn != nullptr && bn_scenes > 0;
+      SSTG_CUDA_TRY(launch_pdl(kern, grid + (with_bn ? 1 : 0), X_THREADS, smem, st, H, seg_off, tile_off, n_tiles, Wp,
+                               params, out, Usave, Xsave, layer_stride, bn_stats, bn_scenes, bn_momentum,
+                               with_bn ? bn : nullptr),
                     "txpcnn launch");
       return SSTG_OK;
     }
-    kern<<<grid, X_THREADS, smem, st>>>(H, seg_off, tile_off, n_tiles, Wp, params, out, Usave, Xsave, layer_stride);
+    kern<<<grid, X_THREADS, smem, st>>>(H, seg_off, tile_off, n_tiles, Wp, params, out, Usave, Xsave, layer_stride,
+                                        nullptr, 0, 0.0, nullptr);
     SSTG_CUDA_TRY(cudaGetLastError(), "txpcnn launch");
     return SSTG_OK;
   };
