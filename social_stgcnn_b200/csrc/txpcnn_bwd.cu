@@ -146,8 +146,10 @@ __device__ __forceinline__ void dw_unit(const float* __restrict__ DU, const floa
 // of x and 9 packed accumulators (18 weight gradients), the three slices are added in slice order through
 // two shuffles per value, and lane 0 of the trio updates the CTA accumulator entries only it ever touches.
 // 10 trios per warp, 8 warps: 72 units (12 input channels) in one pass.
+// The bias gradients db[co] = sum of du over the plane ride along in the trios of input channel 0.
 __device__ __forceinline__ void dw_pair_slices(const float* __restrict__ DU, const float* __restrict__ XT, int Wp,
-                                               int c_end, int cin, int warp, int lane, float* __restrict__ gw) {
+                                               int c_end, int cin, int warp, int lane, float* __restrict__ gw,
+                                               float* __restrict__ gb) {
   const int grp = lane / 3, sl = lane - grp * 3;
   const int pu = warp * 10 + grp;
   const bool act = lane < 30 && pu < 6 * cin;
@@ -157,7 +159,7 @@ __device__ __forceinline__ void dw_pair_slices(const float* __restrict__ DU, con
   int c_hi = c_lo + per - 1;
   if (c_hi > c_end) c_hi = c_end;
   if (!act) c_hi = 0;
-  float2 acc[9];
+  float2 acc[9], accb = make_float2(0.f, 0.f);
 #pragma unroll
   for (int k = 0; k < 9; ++k) acc[k] = make_float2(0.f, 0.f);
   const float* xr = XT + (ci * 5) * Wp;
@@ -169,12 +171,18 @@ __device__ __forceinline__ void dw_pair_slices(const float* __restrict__ DU, con
     x0[h] = xr[h * Wp + c_lo - 1];
     x1[h] = xr[h * Wp + c_lo];
   }
+#pragma unroll 2
   for (int c = c_lo; c <= c_hi; ++c) {
     float2 d[5];
 #pragma unroll
     for (int h = 0; h < 5; ++h) {
       x2[h] = xr[h * Wp + c + 1];
       d[h] = make_float2(d0[h * Wp + c], d1[h * Wp + c]);
+    }
+#pragma unroll
+    for (int h = 0; h < 5; ++h) {
+      accb.x += d[h].x;
+      accb.y += d[h].y;
     }
 #pragma unroll
     for (int kh = 0; kh < 3; ++kh)
@@ -202,6 +210,14 @@ __device__ __forceinline__ void dw_pair_slices(const float* __restrict__ DU, con
     if (act && sl == 0) {
       g0[k] += ax;
       g1[k] += ay;
+    }
+  }
+  {
+    const float bx = (accb.x + __shfl_down_sync(0xffffffffu, accb.x, 1)) + __shfl_down_sync(0xffffffffu, accb.x, 2);
+    const float by = (accb.y + __shfl_down_sync(0xffffffffu, accb.y, 1)) + __shfl_down_sync(0xffffffffu, accb.y, 2);
+    if (act && sl == 0 && ci == 0) {
+      gb[2 * p] += bx;
+      gb[2 * p + 1] += by;
     }
   }
 }
@@ -341,11 +357,11 @@ txpcnn_bwd_kernel(const float* __restrict__ dOut, const float* __restrict__ Usav
       // ---- weight and bias gradients of layer l
       float* gw = gacc + (w_base(l) - P_TP0_W);
       if (cgs > 1) {
-        dw_pair_slices(DU, XT, Wp, c_end, cin, warp, lane, gw);
+        dw_pair_slices(DU, XT, Wp, c_end, cin, warp, lane, gw, gacc + (b_base(l) - P_TP0_W));
       } else {
         for (int unit = warp; unit < 2 * cin; unit += 8) dw_unit(DU, XT, Wp, c_end, unit >> 1, unit & 1, cin, lane, gw);
       }
-      for (int co = warp; co < 12; co += 8) {
+      for (int co = warp; co < 12 && cgs == 1; co += 8) {
         float sb_ = 0.f;
         for (int c = 1 + lane; c <= c_end; c += 32)
 #pragma unroll
