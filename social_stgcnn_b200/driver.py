@@ -105,6 +105,8 @@ def train_epoch(dataset, engine: E.TrainEngine, batch_size: int = 128, lr: float
     bounds = list(range(0, S, batch_size)) + [S]
     groups = [order[a:b] for a, b in zip(bounds[:-1], bounds[1:])]
     plans = E.plan_groups([n_all[g] for g in groups], dev) if trainer is None else None
+    if trainer is not None and hasattr(trainer, "prepare"):
+        trainer.prepare([n_all[g] for g in groups], batch_size)
     losses = torch.zeros(len(groups), dtype=torch.float32, device=dev)
     for gi, (a, b) in enumerate(zip(bounds[:-1], bounds[1:])):
         # (a trailing group of ONE scene has no scored scene: zero loss, zero gradient -- the

@@ -264,7 +264,7 @@ class PeerExchange:
 class _ShardedGroup:
     """Host metadata of one optimiser group as this rank sees it (cached per pedestrian-count vector)."""
 
-    def __init__(self, n_peds, batch_size, world, rank, dev):
+    def __init__(self, n_peds, batch_size, world, rank, dev, upload: bool = True):
         from . import engine as E
         self.n_peds = n_peds
         self.S_all = int(n_peds.size)
@@ -272,11 +272,40 @@ class _ShardedGroup:
         seg = np.concatenate([[0], np.cumsum(n_peds)]).astype(np.int64)
         self.p_lo, self.p_hi = int(seg[self.lo]), int(seg[self.hi])
         self.w_all = E.group_weights(self.S_all, batch_size)
-        self.plan = E.ScenePlan(n_peds[self.lo:self.hi]) if self.hi > self.lo else None
-        self.w_dev = torch.from_numpy(np.ascontiguousarray(self.w_all[self.lo:self.hi])).to(dev) \
-            if self.plan is not None else None
-        self.seg_all_dev = torch.from_numpy(seg.astype(np.int32)).to(dev)
+        self._seg32 = seg.astype(np.int32)
+        self._w_local = np.ascontiguousarray(self.w_all[self.lo:self.hi], np.float32)
         self.full_plan = None
+        self.plan = self.w_dev = self.seg_all_dev = None
+        if upload:                      # one group at a time: three small host->device copies
+            self.plan = E.ScenePlan(n_peds[self.lo:self.hi]) if self.hi > self.lo else None
+            self.w_dev = torch.from_numpy(self._w_local).to(dev) if self.plan is not None else None
+            self.seg_all_dev = torch.from_numpy(self._seg32).to(dev)
+
+    @staticmethod
+    def upload_many(groups, dev):
+        """Device side of many groups (an epoch) in TWO host->device copies: the local plans' offset tables
+        (engine.plan_groups) and one arena holding every group's global seg_off and local loss weights."""
+        from . import engine as E
+        todo = [g for g in groups if g.seg_all_dev is None]
+        if not todo:
+            return
+        local = [g for g in todo if g.hi > g.lo]
+        for g, pl in zip(local, E.plan_groups([g.n_peds[g.lo:g.hi] for g in local], dev)):
+            g.plan = pl
+        offs, total = [], 0
+        for g in todo:
+            o_s = total
+            o_w = o_s + ((g._seg32.size + 3) & ~3)
+            total = o_w + ((g._w_local.size + 3) & ~3)
+            offs.append((o_s, o_w))
+        host = np.zeros(max(total, 4), np.int32)
+        for g, (o_s, o_w) in zip(todo, offs):
+            host[o_s:o_s + g._seg32.size] = g._seg32
+            host[o_w:o_w + g._w_local.size] = g._w_local.view(np.int32)
+        buf = torch.from_numpy(host).to(dev)
+        for g, (o_s, o_w) in zip(todo, offs):
+            g.seg_all_dev = buf[o_s:o_s + g._seg32.size]
+            g.w_dev = buf[o_w:o_w + g._w_local.size].view(torch.float32) if g.hi > g.lo else None
 
 
 class DistributedTrainer:
@@ -326,11 +355,27 @@ class DistributedTrainer:
                 self.peer = None
         self.exchange = "peer" if self.peer is not None else ("nccl" if world > 1 else "none")
 
+    def prepare(self, n_peds_list, batch_size: int):
+        """Host preparation of many groups at once (driver.train_epoch calls it with the epoch's groups): their
+        offset tables, global segment offsets and loss weights reach the device in two copies instead of
+        three per group."""
+        world, rank = self._wr or _world(self.group)
+        new = []
+        for n in n_peds_list:
+            n = np.ascontiguousarray(np.asarray(n, np.int32).reshape(-1))
+            key = (n.tobytes(), batch_size)
+            if key not in self._groups:
+                if len(self._groups) >= 4096:
+                    self._groups.clear()
+                g = self._groups[key] = _ShardedGroup(n, batch_size, world, rank, self.engine.device, upload=False)
+                new.append(g)
+        _ShardedGroup.upload_many(new, self.engine.device)
+
     def _group(self, n_peds, batch_size):
         key = (n_peds.tobytes(), batch_size)
         g = self._groups.get(key)
         if g is None:
-            if len(self._groups) >= 256:
+            if len(self._groups) >= 4096:
                 self._groups.clear()
             world, rank = self._wr or _world(self.group)
             g = self._groups[key] = _ShardedGroup(n_peds, batch_size, world, rank, self.engine.device)

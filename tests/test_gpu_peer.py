@@ -159,6 +159,25 @@ def _rank_main(rank, world, port, params, bn, ret):
         both = [torch.empty_like(blob) for _ in range(world)]
         dist.all_gather(both, blob)
         assert all(torch.equal(both[0], b) for b in both)                       # replicas: same bits
+        # ---- a whole shuffled epoch through the driver (batched host preparation, DistributedTrainer.prepare)
+        from social_stgcnn_b200 import driver
+        n_all = np.concatenate([g[0] for g in groups])
+        obs_all = torch.from_numpy(np.concatenate([g[1] for g in groups])).to(dev)
+        pred_all = torch.from_numpy(np.concatenate([g[2] for g in groups])).to(dev)
+
+        class Split:
+            packed = {"device": dev, "obs_rel": obs_all, "pred_rel": pred_all}
+            plan_obs = sstg.ScenePlan(n_all)
+
+            def __len__(self):
+                return int(n_all.size)
+
+        order = np.random.default_rng(4).permutation(int(n_all.size))
+        la = driver.train_epoch(Split(), e_peer, scenes, lr, order=order, trainer=t_peer)
+        lb = driver.train_epoch(Split(), e_one, scenes, lr, order=order)
+        assert abs(la - lb) <= 1e-5 * abs(lb) + 1e-7, (la, lb)
+        assert float((e_peer.params - e_one.params).abs().max()) <= 2e-4 * scale * lr + 1e-9
+        assert torch.allclose(e_peer.bn, e_one.bn, rtol=1e-5, atol=1e-7)
         t_peer.peer.close()
         ret[rank] = "ok"
     except Exception as e:
