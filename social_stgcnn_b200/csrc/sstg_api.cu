@@ -2,6 +2,7 @@
 // host-side planning, and dispatch to the kernel launchers.  No torch types, no
 // allocation, no synchronisation.
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "sstg_common.cuh"
@@ -16,6 +17,11 @@ void note_cuda_error(cudaError_t e, const char* where) {
 }
 
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+bool pdl_enabled() {
+  const char* e = std::getenv("SSTG_NO_PDL");
+  return !(e && e[0] == '1');
+}
 
 }  // namespace sstg
 

@@ -115,6 +115,8 @@ __device__ __forceinline__ float inv_dist(float sq) { return sq >= 1.17549435e-3
 
 #endif  // __CUDACC__
 
+bool pdl_enabled();  // sstg_api.cu: false when the environment has SSTG_NO_PDL=1 (read at every launch)
+
 #ifdef __CUDACC__
 // <<<grid, block, smem, st>>> with programmatic stream serialization allowed (the kernel must call pdl_wait()).
 template <class... KArgs, class... Args>
@@ -129,7 +131,7 @@ inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, siz
   at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   at[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = at;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;   // SSTG_NO_PDL=1: plain stream order (A/B runs, tests)
   return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
 }
 #endif
