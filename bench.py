@@ -274,6 +274,48 @@ def run_ragged_leg(dev, steps=5, num_scenes=65536):
 
 
 # ---------------------------------------------------------------------------------
+# large-scene leg (BASELINE.json config 4): 256 pedestrians per scene, N x N aggregation stress
+# ---------------------------------------------------------------------------------
+def run_large_leg(dev, steps=5, num_scenes=2048, n_peds=256):
+    """scenes/s of graph build + forward + 20-sample ADE/FDE on scenes of 256 pedestrians (A is 2 MB per
+    scene: the st_gcn kernel streams it once), and the st_gcn kernel's share of the HBM roofline there."""
+    import torch
+    import social_stgcnn_b200 as sstg
+    from social_stgcnn_b200 import engine as E
+    params, bn = load_weights()
+    eng = sstg.InferenceEngine(params, bn, dev)
+    obs, pred, last = synth_batch(num_scenes, n_peds, 777)
+    obs, pred, last = obs.to(dev), pred.to(dev), last.to(dev)
+    plan = sstg.ScenePlan(np.full(num_scenes, n_peds, np.int32))
+    dp = plan.on(dev)
+
+    def timed(fn):
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / steps
+
+    ms = timed(lambda: eng.infer(plan, obs, pred, last, K_SAMPLES, seed=1, want_vtr=False))
+    V, A = E.graph_build(dp, obs, 8)
+    prm, bnb = eng.params, eng.bn
+    H = torch.empty(plan.P * 40, dtype=torch.float32, device=dev)
+    ms_s = timed(lambda: E.stgcn_forward(dp, V, A, prm, bnb, H=H))
+    bytes_s = (64 * n_peds + 32 * n_peds * n_peds + 160 * n_peds) * num_scenes
+    peak, _ = measured_peak_gbs()
+    gbs = bytes_s / (ms_s * 1e-3) / 1e9
+    return {"scenes": num_scenes, "peds_per_scene": n_peds, "scenes_per_s": num_scenes / (ms * 1e-3), "ms_per_step": ms,
+            "stgcn_GBps": gbs, "stgcn_frac_of_hbm": gbs / peak if peak else None,
+            "what": "graph build + st_gcn + TXP-CNN + 20-sample ADE/FDE, device-resident, A materialised "
+                    f"({plan.a_floats * 4 / 1e9:.1f} GB per step: larger than L2)"}
+
+
+# ---------------------------------------------------------------------------------
 # training leg (BASELINE.json config 2): optimiser groups of 128 ragged scenes
 # ---------------------------------------------------------------------------------
 def synth_ragged_counts(num_scenes, seed):
@@ -557,12 +599,13 @@ def run_ours(args):
         best = min(best, q0.elapsed_time(q1))
     copy_gbs = 2 * ca.numel() * 4 / (best * 1e-3) / 1e9
     del ca, cb
-    train = graph_leg = ragged_leg = None
+    train = graph_leg = ragged_leg = large_leg = None
     if not args.no_train:
         train = run_train_leg(dev, world, rank, steps=max(20, 10 * args.steps), warmup=5)
         if rank == 0:
             graph_leg = run_graph_leg(dev)
             ragged_leg = run_ragged_leg(dev)
+            large_leg = run_large_leg(dev)
 
     t = torch.tensor([ms_total, ms_e2e, ms_e2e_c, ms_fused], dtype=torch.float64, device=dev)
     red = torch.tensor([sum_a, sum_f, float(plan.P)], dtype=torch.float64, device=dev)
@@ -621,6 +664,7 @@ def run_ours(args):
             "train": train,
             "graph_construction": graph_leg,
             "ragged_inference": ragged_leg,
+            "large_scenes_256": large_leg,
             "clocks": sampler.result(),
             "result": {"ade": red[0].item() / red[2].item(), "fde": red[1].item() / red[2].item(),
                        "peds": int(red[2].item())},
