@@ -274,6 +274,42 @@ def run_ragged_leg(dev, steps=5, num_scenes=65536):
 
 
 # ---------------------------------------------------------------------------------
+# ETH test split through the drop-in API (BASELINE.json config 1): the reference's own CPU-runnable case
+# ---------------------------------------------------------------------------------
+def run_eth_leg(dev):
+    """test.py's job on the shipped eth/test file (70 scenes, 181 pedestrians) with the eth checkpoint:
+    TrajectoryDataset (file parsing + windowing + graph build) and driver.evaluate (forward + KSTEPS=20
+    sampling + ADE/FDE with the reference's fp64 rounding islands), wall clock incl. every copy."""
+    import time
+    import torch
+    import social_stgcnn_b200 as sstg
+    from social_stgcnn_b200 import driver
+    from social_stgcnn_b200.utils import TrajectoryDataset
+    path = os.path.join(ROOT, "tests", "golden", "datasets", "eth", "test") + "/"
+    if not os.path.isdir(path):
+        return None
+    params, bn = load_weights()
+    eng = sstg.InferenceEngine(params, bn, dev)
+    d = TrajectoryDataset(path, obs_len=8, pred_len=12, skip=1, norm_lap_matr=True)      # warm (page cache, kernels)
+    driver.evaluate(d, eng, KSTEPS=K_SAMPLES, seed=0)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    d = TrajectoryDataset(path, obs_len=8, pred_len=12, skip=1, norm_lap_matr=True)
+    torch.cuda.synchronize()
+    t1 = time.perf_counter()
+    reps = 20
+    for i in range(reps):
+        ade_, fde_, _ = driver.evaluate(d, eng, KSTEPS=K_SAMPLES, seed=i)
+    torch.cuda.synchronize()
+    t2 = time.perf_counter()
+    return {"scenes": len(d), "pedestrians": int(d.obs_traj.shape[0]), "dataset_build_ms": (t1 - t0) * 1e3,
+            "evaluate_ms": (t2 - t1) / reps * 1e3, "scenes_per_s_evaluate": len(d) * reps / (t2 - t1),
+            "ade": ade_, "fde": fde_,
+            "what": "utils.TrajectoryDataset + driver.evaluate (= test.py:18-127) on datasets/eth/test, eth checkpoint; "
+                    "the unmodified reference needs ~10 minutes for its five test splits on 8 CPU cores (SURVEY 8c)"}
+
+
+# ---------------------------------------------------------------------------------
 # large-scene leg (BASELINE.json config 4): 256 pedestrians per scene, N x N aggregation stress
 # ---------------------------------------------------------------------------------
 def run_large_leg(dev, steps=5, num_scenes=2048, n_peds=256):
@@ -599,13 +635,14 @@ def run_ours(args):
         best = min(best, q0.elapsed_time(q1))
     copy_gbs = 2 * ca.numel() * 4 / (best * 1e-3) / 1e9
     del ca, cb
-    train = graph_leg = ragged_leg = large_leg = None
+    train = graph_leg = ragged_leg = large_leg = eth_leg = None
     if not args.no_train:
         train = run_train_leg(dev, world, rank, steps=max(20, 10 * args.steps), warmup=5)
         if rank == 0:
             graph_leg = run_graph_leg(dev)
             ragged_leg = run_ragged_leg(dev)
             large_leg = run_large_leg(dev)
+            eth_leg = run_eth_leg(dev)
 
     t = torch.tensor([ms_total, ms_e2e, ms_e2e_c, ms_fused], dtype=torch.float64, device=dev)
     red = torch.tensor([sum_a, sum_f, float(plan.P)], dtype=torch.float64, device=dev)
@@ -665,6 +702,7 @@ def run_ours(args):
             "graph_construction": graph_leg,
             "ragged_inference": ragged_leg,
             "large_scenes_256": large_leg,
+            "eth_test_split": eth_leg,
             "clocks": sampler.result(),
             "result": {"ade": red[0].item() / red[2].item(), "fde": red[1].item() / red[2].item(),
                        "peds": int(red[2].item())},
