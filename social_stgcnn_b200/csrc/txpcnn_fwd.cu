@@ -134,7 +134,7 @@ txpcnn_fwd_kernel(const float* __restrict__ Hin, const int32_t* __restrict__ seg
     // Training tiles are small (one ~10-pedestrian scene per CTA) and the step is latency-bound: a tile of
     // <= 64 columns spreads each column's convolution over 2 or 4 lanes (slices of the input channels,
     // butterfly-summed so that all lanes of a column hold the same bits).  CTA-uniform.
-    const int cgs = !SAVE ? 1 : (cols <= X_COLS / 4 ? 4 : (cols <= X_COLS / 2 ? 2 : 1));
+    const int cgs = (!SAVE || JX != 1) ? 1 : (cols <= X_COLS / 4 ? 4 : (cols <= X_COLS / 2 ? 2 : 1));
     const int qt = cgs == 4 ? (idx >> 2) : (cgs == 2 ? (idx >> 1) : idx);
     const int cg = idx & (cgs - 1);
     __syncthreads();  // previous tile fully written out / weights visible
@@ -191,7 +191,7 @@ txpcnn_fwd_kernel(const float* __restrict__ Hin, const int32_t* __restrict__ seg
 #pragma unroll
         for (int pr = 0; pr < 3; ++pr) {
           float2 b = make_float2(sm.bias[l][half * 6 + 2 * pr], sm.bias[l][half * 6 + 2 * pr + 1]);
-          if (cg != 0) b = make_float2(0.f, 0.f);  // the bias enters the butterfly sum once
+          if (cgs != 1) b = make_float2(0.f, 0.f);  // split columns: the owner of an output adds the bias
 #pragma unroll
           for (int h = 0; h < 5; ++h) acc[u][pr][h] = b;
         }
@@ -216,18 +216,79 @@ txpcnn_fwd_kernel(const float* __restrict__ Hin, const int32_t* __restrict__ seg
                 conv_column2<6>(act, Wp, sc[u], wl, half, acc[u], cg * 6);
             }
           }
+        }
+      }
+      if (SAVE && JX == 1 && cgs != 1) {
+        // ---- split column: the 2 / 4 lanes of a column reduce-scatter their partial sums (a lane hands over the
+        // half its partner keeps), so each lane ends up OWNING 8 / 4 of the column's 15 (channel pair, row) outputs
+        // and does the activation, residual, saves and write-back for those only.
+        float2 f[16];
 #pragma unroll
-          for (int pr = 0; pr < 3; ++pr)
+        for (int pr = 0; pr < 3; ++pr)
 #pragma unroll
-            for (int h = 0; h < 5; ++h) {
-              acc[u][pr][h].x += __shfl_xor_sync(0xffffffffu, acc[u][pr][h].x, 1);
-              acc[u][pr][h].y += __shfl_xor_sync(0xffffffffu, acc[u][pr][h].y, 1);
-              if (cgs == 4) {
-                acc[u][pr][h].x += __shfl_xor_sync(0xffffffffu, acc[u][pr][h].x, 2);
-                acc[u][pr][h].y += __shfl_xor_sync(0xffffffffu, acc[u][pr][h].y, 2);
+          for (int h = 0; h < 5; ++h) f[pr * 5 + h] = acc[0][pr][h];
+        f[15] = make_float2(0.f, 0.f);
+        const bool up1 = (cg & 1) != 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float2 send = up1 ? f[j] : f[j + 8], keep = up1 ? f[j + 8] : f[j];
+          f[j].x = keep.x + __shfl_xor_sync(0xffffffffu, send.x, 1);
+          f[j].y = keep.y + __shfl_xor_sync(0xffffffffu, send.y, 1);
+        }
+        int base = up1 ? 8 : 0, nown = 8;
+        if (cgs == 4) {
+          const bool up2 = (cg & 2) != 0;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float2 send = up2 ? f[j] : f[j + 4], keep = up2 ? f[j + 4] : f[j];
+            f[j].x = keep.x + __shfl_xor_sync(0xffffffffu, send.x, 2);
+            f[j].y = keep.y + __shfl_xor_sync(0xffffffffu, send.y, 2);
+          }
+          base += up2 ? 4 : 0;
+          nown = 4;
+        }
+        PHASE_XF(3 + 2 * l);
+        const float sl = l < 4 ? sm.slope[l] : 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int sidx = base + j;
+          if (j < nown && sidx < 15 && on[0]) {
+            const int pr = sidx / 5, h = sidx - pr * 5;
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const int co = half * 6 + 2 * pr + e, row = co * 5 + h;
+              float& a = e ? f[j].y : f[j].x;
+              a += sm.bias[l][co];
+              if (l < 4) {
+                float v = prelu(a, sl);
+                if (l > 0) v += act[row * Wp + sc[0]];  // residual (model.py:192)
+                const long long g = l * layer_stride + gO[0] + static_cast<long long>(row) * gN[0];
+                Usave[g] = a;
+                Xsave[g] = v;
+                a = v;
+              } else {
+                out[gO[0] + static_cast<long long>(row) * gN[0]] = a;
               }
             }
+          }
         }
+        if (l < 4) {
+          __syncthreads();  // everyone has read the old activations
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int sidx = base + j;
+            if (j < nown && sidx < 15 && on[0]) {
+              const int pr = sidx / 5, h = sidx - pr * 5;
+              act[((half * 6 + 2 * pr) * 5 + h) * Wp + sc[0]] = f[j].x;
+              act[((half * 6 + 2 * pr + 1) * 5 + h) * Wp + sc[0]] = f[j].y;
+            }
+          }
+          __syncthreads();
+          PHASE_XF(4 + 2 * l);
+        } else {
+          PHASE_XF(12);
+        }
+        continue;
       }
       PHASE_XF(3 + 2 * l);
       if (l < 4) {
