@@ -281,9 +281,14 @@ txpcnn_bwd_kernel(const float* __restrict__ dOut, const float* __restrict__ Usav
     const int nsc = s_hi - s_lo;
     const int c_end = cols + nsc - 1;  // last data column of the shared tile
     // lanes per column of the transposed convolution (CTA-uniform): 4 / 2 for small tiles, else 1
-    const int cgs = cols <= X_COLS / 4 ? 4 : (cols <= X_COLS / 2 ? 2 : 1);
+    const int cgs = JX != 1 ? 1 : (cols <= X_COLS / 4 ? 4 : (cols <= X_COLS / 2 ? 2 : 1));
     const int qt = cgs == 4 ? (idx >> 2) : (cgs == 2 ? (idx >> 1) : idx);
     const int cg = idx & (cgs - 1);
+    // split columns: after the reduce-scatter of the transposed convolution, lane `cg` OWNS entries
+    // [own_base, own_base + own_n) of the column's 15 (channel pair, feature row) entries -- it alone keeps
+    // their dL/dx, loads their pre-activations and writes their du (entry e <-> pair e / 5, row e % 5).
+    const int own_n = cgs == 4 ? 4 : 8;
+    const int own_base = ((cg & 1) ? 8 : 0) + ((cgs == 4 && (cg & 2)) ? 4 : 0);
     __syncthreads();
     for (int q = tid; q < cols; q += X_THREADS) {
       int j = 0;
@@ -315,6 +320,23 @@ txpcnn_bwd_kernel(const float* __restrict__ dOut, const float* __restrict__ Usav
       const int sb = on[u] ? sm.sbase[q] : 0;
       gO[u] = static_cast<long long>(p_lo + sb) * 60 + (q - sb);
       // layer 4 (tpcnn_ouput, no activation): du_4 = dOut
+      if (JX == 1 && cgs != 1) {  // split column: only the owned entries (kept in the first own_n slots of G)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int e = own_base + j;
+          const bool mine = j < own_n && e < 15 && on[u];
+          const int pr = e / 5, h = e - pr * 5;
+          const int r0 = (half * 6 + 2 * pr) * 5 + h;
+          float2& Gj = G[u][j / 5][j % 5];
+          Gj.x = mine ? __ldg(dOut + gO[u] + static_cast<long long>(r0) * gN[u]) : 0.f;
+          Gj.y = mine ? __ldg(dOut + gO[u] + static_cast<long long>(r0 + 5) * gN[u]) : 0.f;
+          if (mine) {
+            DU[r0 * Wp + sc[u]] = Gj.x;
+            DU[(r0 + 5) * Wp + sc[u]] = Gj.y;
+          }
+        }
+        continue;
+      }
 #pragma unroll
       for (int co = 0; co < 6; ++co)
 #pragma unroll
@@ -388,28 +410,90 @@ txpcnn_bwd_kernel(const float* __restrict__ dOut, const float* __restrict__ Usav
         if (cgs == 1) {
           if (on[u]) conv_column2<12>(DU, Wp, sc[u], sm.wT + l * X_WL, half, T[u]);
         } else {
-          // a slice of the 12 channels per lane, then a butterfly over the 2 / 4 lanes of the column:
-          // fp32 addition commutes, so every lane ends with the same bits
+          // a slice of the 12 channels per lane, then a reduce-scatter over the 2 / 4 lanes of the column: at each
+          // step a lane hands over the half of the entries its partner keeps; the sums land in T's first slots
           if (on[u]) {
             if (cgs == 4) conv_column2<3>(DU, Wp, sc[u], sm.wT + l * X_WL, half, T[u], cg * 3);
             else conv_column2<6>(DU, Wp, sc[u], sm.wT + l * X_WL, half, T[u], cg * 6);
           }
+          float2 f[16];
 #pragma unroll
-          for (int pr = 0; pr < 3; ++pr)
+          for (int e = 0; e < 15; ++e) f[e] = T[u][e / 5][e % 5];
+          f[15] = make_float2(0.f, 0.f);
+          const bool up1 = (cg & 1) != 0;
 #pragma unroll
-            for (int h = 0; h < 5; ++h) {
-              T[u][pr][h].x += __shfl_xor_sync(0xffffffffu, T[u][pr][h].x, 1);
-              T[u][pr][h].y += __shfl_xor_sync(0xffffffffu, T[u][pr][h].y, 1);
-              if (cgs == 4) {
-                T[u][pr][h].x += __shfl_xor_sync(0xffffffffu, T[u][pr][h].x, 2);
-                T[u][pr][h].y += __shfl_xor_sync(0xffffffffu, T[u][pr][h].y, 2);
-              }
+          for (int j = 0; j < 8; ++j) {
+            const float2 send = up1 ? f[j] : f[j + 8], keep = up1 ? f[j + 8] : f[j];
+            f[j].x = keep.x + __shfl_xor_sync(0xffffffffu, send.x, 1);
+            f[j].y = keep.y + __shfl_xor_sync(0xffffffffu, send.y, 1);
+          }
+          if (cgs == 4) {
+            const bool up2 = (cg & 2) != 0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float2 send = up2 ? f[j] : f[j + 4], keep = up2 ? f[j + 4] : f[j];
+              f[j].x = keep.x + __shfl_xor_sync(0xffffffffu, send.x, 2);
+              f[j].y = keep.y + __shfl_xor_sync(0xffffffffu, send.y, 2);
             }
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) T[u][j / 5][j % 5] = f[j];
         }
       }
       PHASE(5 + (4 - l) * 6);
       __syncthreads();  // every read of DU for layer l is done
       PHASE(6 + (4 - l) * 6);
+      if (JX == 1 && cgs != 1) {
+        // ---- split column, owner side: entry e = own_base + j lives in slot j of T and G
+        const int kk = l - 1;
+        const float slope_k = l > 0 ? sm.slope[kk] : 0.f;
+        float2 uvo[8];
+        if (l > 0) {  // every load before its first use
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int e = own_base + j;
+            const bool mine = j < own_n && e < 15 && on[0];
+            const int pr = e / 5, h = e - pr * 5;
+            const float* up = Usave + kk * layer_stride + gO[0] + static_cast<long long>((half * 6 + 2 * pr) * 5 + h) * gN[0];
+            uvo[j].x = mine ? __ldg(up) : 1.f;
+            uvo[j].y = mine ? __ldg(up + 5 * gN[0]) : 1.f;
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int e = own_base + j;
+          const bool mine = j < own_n && e < 15 && on[0];
+          const int pr = e / 5, h = e - pr * 5;
+          const int r0 = (half * 6 + 2 * pr) * 5 + h;
+          const float2 Tv = T[0][j / 5][j % 5];
+          if (l == 0) {
+            if (mine) {
+              const int q = qt;
+              const int sb = sm.sbase[q];
+              float* o = dH + static_cast<long long>(p_lo + sb) * 40 + (q - sb);
+              if (r0 < 40) o[static_cast<long long>(r0) * gN[0]] = Tv.x;
+              if (r0 + 5 < 40) o[static_cast<long long>(r0 + 5) * gN[0]] = Tv.y;
+            }
+            continue;
+          }
+          float2& Gj = G[0][j / 5][j % 5];
+          const float gx = (l == 4) ? Tv.x : Gj.x + Tv.x, gy = (l == 4) ? Tv.y : Gj.y + Tv.y;
+          Gj = make_float2(gx, gy);
+          if (mine) {
+            const bool px = uvo[j].x > 0.f, py = uvo[j].y > 0.f;
+            if (!px) dsl[kk] = fmaf(gx, uvo[j].x, dsl[kk]);
+            if (!py) dsl[kk] = fmaf(gy, uvo[j].y, dsl[kk]);
+            DU[r0 * Wp + sc[0]] = px ? gx : slope_k * gx;
+            DU[(r0 + 5) * Wp + sc[0]] = py ? gy : slope_k * gy;
+          }
+        }
+        if (l == 0) break;
+        PHASE(7 + (4 - l) * 6);
+        cp_async_wait_all();
+        PHASE(8 + (4 - l) * 6);
+        __syncthreads();
+        continue;
+      }
       if (l == 0) {
 #pragma unroll
         for (int u = 0; u < JX; ++u)
