@@ -153,7 +153,7 @@ stgcn_train_fwd_kernel(const float* __restrict__ V, const float* __restrict__ A,
 #pragma unroll
       for (int j = 0; j < NJ; ++j) y[c][j] = 0.f;
     const float* At = A + a_off[s] + static_cast<size_t>(t) * N * N;
-#pragma unroll 8
+#pragma unroll 16
     for (int v = 0; v < N; ++v) {
       const float4 g4 = *reinterpret_cast<const float4*>(gw + v * 8);
       const float g5 = gw[v * 8 + 4];
@@ -482,7 +482,7 @@ stgcn_train_bwd_kernel(const float* __restrict__ V, const float* __restrict__ A,
     __syncwarp();
     PHASE_ST(7);
     // ---- phase E: d_g[c, t, v] = sum_w d_y[c, t, w] A[t, v, w];  dWg, dbg.
-    // Lanes <-> source nodes v, each lane walks ITS row of A (w ascending, 8 loads in flight) against
+    // Lanes <-> source nodes v, each lane walks ITS row of A (w ascending, 16 loads in flight) against
     // d_y broadcast from shared memory: no cross-lane reduction and no load->shuffle chain per node --
     // the per-node latency chain was what set the duration of a small group.  A[t] is at most 16 KB per
     // warp at N = 64 and stays in L1 across the strided row walk.
@@ -492,12 +492,21 @@ stgcn_train_bwd_kernel(const float* __restrict__ V, const float* __restrict__ A,
       const float* row = At + static_cast<size_t>(v) * N;
       float pg[C] = {0.f, 0.f, 0.f, 0.f, 0.f};
       int w = 0;
-      for (; w + 8 <= N; w += 8) {
-        float a[8];
+      for (; w + 16 <= N; w += 16) {
+        float a[16];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) a[j] = __ldg(row + w + j);
+        for (int j = 0; j < 16; ++j) a[j] = __ldg(row + w + j);
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
+        for (int j = 0; j < 16; ++j)
+#pragma unroll
+          for (int c = 0; c < C; ++c) pg[c] = fmaf(dyt[c * T_OBS * NP + w + j], a[j], pg[c]);
+      }
+      for (; w + 4 <= N; w += 4) {
+        float a[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) a[j] = __ldg(row + w + j);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
 #pragma unroll
           for (int c = 0; c < C; ++c) pg[c] = fmaf(dyt[c * T_OBS * NP + w + j], a[j], pg[c]);
       }
