@@ -172,32 +172,48 @@ class PeerExchange:
             nbytes = int(lib.sstg_peer_mailbox_bytes(self.world, self.max_scenes))
             if nbytes < 0:
                 L.check(nbytes, "sstg_peer_mailbox_bytes")
-            own, handle = C.c_void_p(), C.create_string_buffer(64)
-            with torch.cuda.device(self.device):
-                L.check(lib.sstg_peer_alloc(nbytes, C.byref(own), handle), "sstg_peer_alloc")
-            self._own = own.value
+            # Every rank takes part in the same two exchanges whatever happens locally (a rank that failed sends
+            # its error text instead of a handle), so a failure surfaces on ALL ranks instead of leaving the
+            # others stuck in a collective.
             import socket
-            mine = (socket.gethostname(), handle.raw)
+            own, handle, err = C.c_void_p(), C.create_string_buffer(64), None
+            try:
+                with torch.cuda.device(self.device):
+                    L.check(lib.sstg_peer_alloc(nbytes, C.byref(own), handle), "sstg_peer_alloc")
+                self._own = own.value
+            except Exception as e:                                   # noqa: BLE001 -- reported to every rank below
+                err = f"rank {self.rank}: {e}"
+            mine = (socket.gethostname(), handle.raw if err is None else None, err)
             everyone = [None] * self.world
             if self.world > 1:
                 dist.all_gather_object(everyone, mine, group=group)
             else:
                 everyone = [mine]
-            if any(h[0] != mine[0] for h in everyone):
-                raise RuntimeError("PeerExchange needs all ranks on one node (peer memory over NVLink)")
+            errs = [h[2] for h in everyone if h[2]]
+            if not errs and any(h[0] != mine[0] for h in everyone):
+                errs = ["PeerExchange needs all ranks on one node (peer memory over NVLink)"]
             ptrs = []
-            for r, (_, raw) in enumerate(everyone):
-                if r == self.rank:
-                    ptrs.append(self._own)
-                    continue
-                q = C.c_void_p()
-                with torch.cuda.device(self.device):
-                    L.check(lib.sstg_peer_open(raw, C.byref(q)), f"sstg_peer_open(rank {r})")
-                self._opened.append(q.value)
-                ptrs.append(q.value)
-            if self.world > 1:
-                torch.cuda.synchronize(self.device)
-                dist.barrier(group=group)            # nobody stores into a mailbox that is not mapped and zeroed yet
+            if not errs:
+                try:
+                    for r, (_, raw, _e) in enumerate(everyone):
+                        if r == self.rank:
+                            ptrs.append(self._own)
+                            continue
+                        q = C.c_void_p()
+                        with torch.cuda.device(self.device):
+                            L.check(lib.sstg_peer_open(raw, C.byref(q)), f"sstg_peer_open(rank {r})")
+                        self._opened.append(q.value)
+                        ptrs.append(q.value)
+                    torch.cuda.synchronize(self.device)
+                except Exception as e:                               # noqa: BLE001
+                    errs = [f"rank {self.rank}: {e}"]
+            if self.world > 1:                   # second exchange doubles as the barrier: nobody stores into a
+                opened = [None] * self.world     # mailbox that is not mapped and zeroed on every rank yet
+                dist.all_gather_object(opened, errs, group=group)
+                errs = [x for lst in opened for x in lst]
+            if errs:
+                self.close()
+                raise RuntimeError("peer-memory exchange unavailable: " + "; ".join(sorted(set(errs))))
         self._boxes = (C.c_void_p * self.world)(*ptrs)
         self.status = torch.zeros(1, dtype=torch.int32, device=self.device)
         self.loss = torch.zeros(1, dtype=torch.float32, device=self.device)
@@ -251,6 +267,8 @@ class PeerExchange:
 
     def close(self):
         lib = L.load()
+        if not self._opened and not self._own and not getattr(self, "_owned_all", None):
+            return
         with torch.cuda.device(self.device):
             torch.cuda.synchronize(self.device)
             for q in self._opened:
