@@ -223,8 +223,10 @@ int sstg_sgd_step(float* params, const float* grad, int32_t n, float lr, float c
                   float* grad_norm_out, void* stream);
 
 /* ---- one optimiser group of train() in ONE call (train.py:38-74 for `batch_size` scenes) --------
- * graph build (obs: V + A; pred: V only) -> sstg_forward_train -> sstg_nll_backward ->
- * sstg_backward -> sstg_bn_running_update -> [sstg_sgd_step if lr != 0], all on `stream`.
+ * Same results as: graph build (obs: V + A) -> sstg_forward_train -> sstg_nll_backward -> sstg_backward ->
+ * sstg_bn_running_update -> [sstg_sgd_step if lr != 0], all on `stream` -- issued as 7 kernels chained by
+ * programmatic dependent launch (the NLL kernel reads pred_rel directly, the BatchNorm recurrence rides in the
+ * TXP-CNN forward launch, gradient reduction + group loss + un-clipped SGD share the last launch).
  *   obs_rel [P,2,8], pred_rel [P,2,12]     TrajectoryDataset.obs_traj_rel / pred_traj_rel rows of the group
  *   params [7563], bn [30]                 updated in place
  *   scene_weight [S]                       1/batch_size, 0 for the unscored last scene (may be NULL = 1)
