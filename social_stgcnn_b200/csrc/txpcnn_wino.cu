@@ -17,7 +17,18 @@
 // scene's last pair computes a second output that is simply not stored.
 // Everything else (whole-scene tiles, five layers in place in one 60-row tile, persistent grid)
 // follows txpcnn_fwd.cu, which remains the kernel for training (SAVE) and for scenes > 128.
+//
+// Filters.  The transformed filters are warp-uniform operands.  CONSTW = true (full grids): they live in a
+// __constant__ bank and reach the FMA pipe as UNIFORM-register pairs (`LDCU.64 UR, c[3][..]` ->
+// `FFMA2 R, R, UR.F32x2, R`): no LDS.128, no staging registers in the inner loop -- 7.8 -> 7.0 ms per 131,072
+// scenes.  For the address to be provably uniform the channel group of a thread must be a compile-time
+// constant, so the main loop is instantiated once per group and selected by a warp-uniform branch.  The bank
+// is refreshed in stream order before every launch (filter transform -> staging at the head of the output
+// buffer -> cudaMemcpyToSymbolAsync): launches with DIFFERENT weights must therefore not overlap on one
+// device (the only global state of the library; SSTG_TXP_FILTERS=smem selects the variant without it).
+// CONSTW = false (small grids, or that knob): every CTA transforms the filters into its shared memory.
 #include <cstdlib>
+#include <type_traits>
 
 #include "txpcnn_common.cuh"
 
@@ -36,8 +47,11 @@ constexpr int W_UL = 12 * 3 * 12 * 4;          // layers 1..4
 constexpr int W_UTOTAL = W_U0 + 4 * W_UL;      // 8064 floats
 constexpr int W_WP_MAX = 200;                  // widest tile row: 128 columns + up to 2 separators per scene
 
-struct WSmem {
-  float U[W_UTOTAL];
+__constant__ float c_U[W_UTOTAL];  // transformed filters of the launch in flight (CONSTW variant)
+
+template <bool CONSTW>
+struct WSmemT {
+  float U[CONSTW ? 4 : W_UTOTAL];
   float bias[5][12];
   float slope[4];
   int s_first[SSTG_XTILE_MAX_SCENES + 1];  // first (odd) shared-memory column of each scene
@@ -49,7 +63,30 @@ struct WSmem {
 
 // W_WP (even, <= W_WP_MAX) is the row stride of the activation tile: the launcher sizes it for the widest
 // tile of the batch, so dense batches (2 scenes of 64 -> 134 columns) fit three CTAs per SM.
-template <int NSPLIT>
+// U[l][ci][kh][co][4] = (g0, (g0+g1+g2)/2, (g0-g1+g2)/2, g2) of filter row kh
+__device__ __forceinline__ float4 wino_filter(const float* __restrict__ params, int i) {
+  int l, r;
+  if (i < W_U0 / 4) {
+    l = 0;
+    r = i;
+  } else {
+    l = 1 + (i - W_U0 / 4) / (W_UL / 4);
+    r = (i - W_U0 / 4) % (W_UL / 4);
+  }
+  const int co = r % 12, kh = (r / 12) % 3, ci = r / 36;
+  const int cin = (l == 0) ? 8 : 12;
+  const int base = (l == 0) ? P_TP0_W : (l == 4 ? P_TPOUT_W : P_TP1_W + (l - 1) * P_TP_STRIDE);
+  const float* g = params + base + (co * cin + ci) * 9 + kh * 3;
+  const float g0 = g[0], g1 = g[1], g2 = g[2];
+  return make_float4(g0, 0.5f * (g0 + g1 + g2), 0.5f * (g0 - g1 + g2), g2);
+}
+
+__global__ void wino_filter_kernel(const float* __restrict__ params, float* __restrict__ U) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < W_UTOTAL / 4) reinterpret_cast<float4*>(U)[i] = wino_filter(params, i);
+}
+
+template <int NSPLIT, bool CONSTW>
 __global__ void __launch_bounds__(NSPLIT * W_PAIRS, 2)
 txpcnn_wino_kernel(const float* __restrict__ Hin, const int32_t* __restrict__ seg_off,
                    const int32_t* __restrict__ tile_off, int n_tiles, const float* __restrict__ params,
@@ -57,6 +94,7 @@ txpcnn_wino_kernel(const float* __restrict__ Hin, const int32_t* __restrict__ se
   constexpr int COT = 12 / NSPLIT;
   constexpr int THREADS = NSPLIT * W_PAIRS;
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  using WSmem = WSmemT<CONSTW>;
   WSmem& sm = *reinterpret_cast<WSmem*>(smem_raw);
   float* act = reinterpret_cast<float*>(smem_raw + ((sizeof(WSmem) + 15) & ~size_t(15)));  // [60][W_WP]
   const int tid = threadIdx.x;
@@ -64,22 +102,9 @@ txpcnn_wino_kernel(const float* __restrict__ Hin, const int32_t* __restrict__ se
   const int pt = tid - grp * W_PAIRS;
   const int co0 = grp * COT;
 
-  // ---- filter transform: U[l][ci][kh][co][4]
-  for (int i = tid; i < W_UTOTAL / 4; i += THREADS) {
-    int l, r;
-    if (i < W_U0 / 4) {
-      l = 0;
-      r = i;
-    } else {
-      l = 1 + (i - W_U0 / 4) / (W_UL / 4);
-      r = (i - W_U0 / 4) % (W_UL / 4);
-    }
-    const int co = r % 12, kh = (r / 12) % 3, ci = r / 36;
-    const int cin = (l == 0) ? 8 : 12;
-    const int base = (l == 0) ? P_TP0_W : (l == 4 ? P_TPOUT_W : P_TP1_W + (l - 1) * P_TP_STRIDE);
-    const float* g = params + base + (co * cin + ci) * 9 + kh * 3;
-    const float g0 = g[0], g1 = g[1], g2 = g[2];
-    reinterpret_cast<float4*>(sm.U)[i] = make_float4(g0, 0.5f * (g0 + g1 + g2), 0.5f * (g0 - g1 + g2), g2);
+  // ---- filter transform into shared memory (the CONSTW variant reads the constant bank instead)
+  if constexpr (!CONSTW) {
+    for (int i = tid; i < W_UTOTAL / 4; i += THREADS) reinterpret_cast<float4*>(sm.U)[i] = wino_filter(params, i);
   }
   if (tid < 60) {
     const int l = tid / 12, co = tid % 12;
@@ -158,11 +183,12 @@ txpcnn_wino_kernel(const float* __restrict__ Hin, const int32_t* __restrict__ se
       for (int c = 0; c < COT; ++c)
 #pragma unroll
         for (int h = 0; h < 5; ++h) Ma[c][h] = Mb[c][h] = make_float2(0.f, 0.f);
-      if (on) {
+      auto main_loop = [&](auto grp_c) {
         // Software pipeline (only 8-12 warps per SM hide latency here, so the loads are rotated by hand):
         // the 10 activation loads of input channel ci+1 and the next NPF filter vectors are in flight
         // while the 10 FFMA2 of the current (kh, channel) step issue.
-        const float* Ul = sm.U + (l == 0 ? 0 : W_U0 + (l - 1) * W_UL) + co0 * 4;
+        constexpr int GRP = decltype(grp_c)::value;  // CONSTW: compile-time group => uniform filter addresses
+        const float* Ul = (CONSTW ? c_U + GRP * COT * 4 : sm.U + co0 * 4) + (l == 0 ? 0 : W_U0 + (l - 1) * W_UL);
         const int CI = (l == 0) ? 8 : 12;
         constexpr int STEPS = 3 * COT, NPF = WINO_NPF;
         const float* a = act + sc0 - 1;  // even offset: aligned float2 loads
@@ -209,6 +235,17 @@ txpcnn_wino_kernel(const float* __restrict__ Hin, const int32_t* __restrict__ se
               }
             }
           }
+        }
+      };
+      if (on) {
+        if constexpr (CONSTW) {
+          static_assert(NSPLIT <= 4, "channel groups");
+          if (grp == 0) main_loop(std::integral_constant<int, 0>{});
+          else if (grp == 1) main_loop(std::integral_constant<int, 1>{});
+          else if (grp == 2) main_loop(std::integral_constant<int, 2 % NSPLIT>{});
+          else main_loop(std::integral_constant<int, 3 % NSPLIT>{});
+        } else {
+          main_loop(std::integral_constant<int, 0>{});
         }
       }
       // ---- output transform, bias, PReLU, residual
@@ -262,23 +299,45 @@ txpcnn_wino_kernel(const float* __restrict__ Hin, const int32_t* __restrict__ se
   }
 }
 
-template <int NSPLIT>
-int launch_wino(const float* H, const int32_t* seg_off, const int32_t* tile_off, int n_tiles, const float* params,
-                float* out, int W_WP, cudaStream_t st) {
-  const size_t smem = ((sizeof(WSmem) + 15) & ~size_t(15)) + sizeof(float) * X_ROWS * W_WP;
-  auto kern = txpcnn_wino_kernel<NSPLIT>;
+template <int NSPLIT, bool CONSTW>
+int launch_wino_v(const float* H, const int32_t* seg_off, const int32_t* tile_off, int n_tiles, const float* params,
+                  float* out, int W_WP, int grid_cap, cudaStream_t st) {
+  const size_t smem = ((sizeof(WSmemT<CONSTW>) + 15) & ~size_t(15)) + sizeof(float) * X_ROWS * W_WP;
+  auto kern = txpcnn_wino_kernel<NSPLIT, CONSTW>;
   SSTG_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)),
                 "txpcnn_wino smem attr");
-  int dev = 0, sms = 148, per_sm = 1;
-  SSTG_CUDA_TRY(cudaGetDevice(&dev), "cudaGetDevice");
-  SSTG_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev), "sm count");
-  SSTG_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NSPLIT * W_PAIRS, smem), "occupancy");
-  if (per_sm < 1) per_sm = 1;
-  const long long want = static_cast<long long>(sms) * per_sm;
-  const int grid = static_cast<int>(n_tiles < want ? n_tiles : want);
+  const int grid = n_tiles < grid_cap ? n_tiles : grid_cap;
+  if (CONSTW) {
+    // refresh the constant bank in stream order; the head of `out` (>= 60 floats per pedestrian, >= n_tiles
+    // pedestrians) is the staging buffer -- the kernel below overwrites it afterwards
+    wino_filter_kernel<<<(W_UTOTAL / 4 + 255) / 256, 256, 0, st>>>(params, out);
+    SSTG_CUDA_TRY(cudaGetLastError(), "wino_filter launch");
+    SSTG_CUDA_TRY(cudaMemcpyToSymbolAsync(c_U, out, sizeof(float) * W_UTOTAL, 0, cudaMemcpyDeviceToDevice, st),
+                  "txpcnn_wino filters -> constant bank");
+  }
   kern<<<grid, NSPLIT * W_PAIRS, smem, st>>>(H, seg_off, tile_off, n_tiles, params, out, W_WP);
   SSTG_CUDA_TRY(cudaGetLastError(), "txpcnn_wino launch");
   return SSTG_OK;
+}
+
+// SSTG_TXP_FILTERS = smem: never use the constant bank (the library's only global state, see the header comment)
+bool wino_const_allowed() {
+  const char* e = getenv("SSTG_TXP_FILTERS");
+  return !(e && e[0] == 's');
+}
+
+template <int NSPLIT>
+int launch_wino(const float* H, const int32_t* seg_off, const int32_t* tile_off, int n_tiles, const float* params,
+                float* out, int W_WP, cudaStream_t st) {
+  int dev = 0, sms = 148;
+  SSTG_CUDA_TRY(cudaGetDevice(&dev), "cudaGetDevice");
+  SSTG_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev), "sm count");
+  const int grid_cap = 2 * sms;  // 255 registers x 128 threads: two CTAs per SM
+  // the constant-bank variant pays a ~6 us refresh per launch: worth it once the persistent grid is full
+  // (then n_tiles * 60 floats of `out` also exceed the 8,064-float staging area by far)
+  if (n_tiles >= grid_cap && wino_const_allowed())
+    return launch_wino_v<NSPLIT, true>(H, seg_off, tile_off, n_tiles, params, out, W_WP, grid_cap, st);
+  return launch_wino_v<NSPLIT, false>(H, seg_off, tile_off, n_tiles, params, out, W_WP, grid_cap, st);
 }
 
 }  // namespace

@@ -244,3 +244,35 @@ def test_inference_kernels_stay_inside_their_buffers(golden, dev):
         assert bool((arena[mask] == SENT).all()), n_list
         assert bool(torch.isfinite(buf["out"][:P * 60]).all()) and bool(torch.isfinite(buf["ade"][:2 * P].view(torch.float64)).all())
         assert float((buf["out"][:P * 60] - buf["out2"][:P * 60]).abs().max()) < 1e-4
+
+
+def test_winograd_constant_bank_filters_equal_shared_memory_filters(golden, dev):
+    """Full grids run the Winograd TXP-CNN with its transformed filters in a __constant__ bank (uniform-register
+    operands), refreshed in stream order before every launch; SSTG_TXP_FILTERS=smem keeps them in shared
+    memory.  Same arithmetic: the outputs must be bit-identical, also when the weights change from one launch
+    to the next on the same stream."""
+    import social_stgcnn_b200 as sstg
+    rng = np.random.default_rng(12)
+    n = np.concatenate([np.full(600, 64), rng.integers(2, 58, 4000)]).astype(np.int32)
+    plan = sstg.ScenePlan(n)
+    assert plan.n_tiles >= 2 * 148                      # the constant-bank variant is selected
+    dp = plan.on(dev)
+    H = torch.from_numpy(rng.standard_normal(plan.P * 40).astype(np.float32)).to(dev)
+    outs = {}
+    for ck in ("eth", "zara1"):
+        prm = torch.from_numpy(golden.params(ck)[0]).to(dev)
+        a = sstg.txpcnn_forward(dp, H, prm).clone()
+        os.environ["SSTG_TXP_FILTERS"] = "smem"
+        try:
+            b = sstg.txpcnn_forward(dp, H, prm).clone()
+        finally:
+            os.environ.pop("SSTG_TXP_FILTERS", None)
+        torch.cuda.synchronize()
+        assert torch.equal(a, b), ck
+        outs[ck] = (prm, a)
+    assert not torch.equal(outs["eth"][1], outs["zara1"][1])
+    # alternate the weights launch after launch without synchronising in between
+    seq = [sstg.txpcnn_forward(dp, H, outs[ck][0]).clone() for ck in ("eth", "zara1", "eth", "zara1")]
+    torch.cuda.synchronize()
+    for got, ck in zip(seq, ("eth", "zara1", "eth", "zara1")):
+        assert torch.equal(got, outs[ck][1]), ck
