@@ -39,15 +39,19 @@ namespace {
 using namespace txp;
 
 #ifndef WINO_NPF
-#define WINO_NPF 3  // filter vectors in flight ahead of their use (tuning knob; 2..4 measured)
+#define WINO_NPF 3  // filter vectors in flight ahead of their use, shared-memory filters (2..6 measured)
 #endif
+#ifndef WINO_NPF_CONST
+#define WINO_NPF_CONST 9   // the same for constant-bank filters: they wait in UNIFORM registers (36 of the warp's 63),
+#endif                     // so a deeper ring costs no vector register.  Both must divide 3 * COT (ring phase).
 constexpr int W_PAIRS = SSTG_XTILE_MAX_PAIRS;  // 64 column pairs per tile
 constexpr int W_U0 = 8 * 3 * 12 * 4;           // layer 0: [ci 8][kh 3][co 12][4]
 constexpr int W_UL = 12 * 3 * 12 * 4;          // layers 1..4
 constexpr int W_UTOTAL = W_U0 + 4 * W_UL;      // 8064 floats
 constexpr int W_WP_MAX = 200;                  // widest tile row: 128 columns + up to 2 separators per scene
 
-__constant__ float c_U[W_UTOTAL];  // transformed filters of the launch in flight (CONSTW variant)
+__constant__ float c_U[W_UTOTAL + 4 * 32];  // transformed filters of the launch in flight (CONSTW variant);
+                                            // the tail pads the prefetch ring's run past the last filter
 
 template <bool CONSTW>
 struct WSmemT {
@@ -190,7 +194,9 @@ txpcnn_wino_kernel(const float* __restrict__ Hin, const int32_t* __restrict__ se
         constexpr int GRP = decltype(grp_c)::value;  // CONSTW: compile-time group => uniform filter addresses
         const float* Ul = (CONSTW ? c_U + GRP * COT * 4 : sm.U + co0 * 4) + (l == 0 ? 0 : W_U0 + (l - 1) * W_UL);
         const int CI = (l == 0) ? 8 : 12;
-        constexpr int STEPS = 3 * COT, NPF = WINO_NPF;
+        constexpr int STEPS = 3 * COT;
+        constexpr int NPF = (CONSTW && STEPS % WINO_NPF_CONST == 0) ? WINO_NPF_CONST : WINO_NPF;
+        static_assert(STEPS % NPF == 0, "the filter ring must keep its phase from one input channel to the next");
         const float* a = act + sc0 - 1;  // even offset: aligned float2 loads
         float2 d01[5], d23[5];
 #pragma unroll
