@@ -55,6 +55,29 @@ __device__ __forceinline__ float sqrt_approx(float x) {
   asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// packed FP32 (sm_100 FADD2 / FMUL2 / FFMA2): two IEEE fp32 operations per issue slot, each component rounded
+// exactly like the scalar instruction -- the sampling loop advances two samples of a pedestrian per instruction
+__device__ __forceinline__ float2 add2(const float2 a, const float2 b) {
+  float2 d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(reinterpret_cast<unsigned long long&>(d))
+      : "l"(reinterpret_cast<const unsigned long long&>(a)), "l"(reinterpret_cast<const unsigned long long&>(b)));
+  return d;
+}
+__device__ __forceinline__ float2 mul2(const float2 a, const float2 b) {
+  float2 d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(reinterpret_cast<unsigned long long&>(d))
+      : "l"(reinterpret_cast<const unsigned long long&>(a)), "l"(reinterpret_cast<const unsigned long long&>(b)));
+  return d;
+}
+__device__ __forceinline__ float2 fma2(const float2 a, const float2 b, const float2 c) {
+  float2 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(reinterpret_cast<unsigned long long&>(d))
+      : "l"(reinterpret_cast<const unsigned long long&>(a)), "l"(reinterpret_cast<const unsigned long long&>(b)),
+        "l"(reinterpret_cast<const unsigned long long&>(c)));
+  return d;
+}
+__device__ __forceinline__ float2 bc2(const float v) { return make_float2(v, v); }
+
 __device__ __forceinline__ float2 box_muller(uint32_t a, uint32_t b) {
   const float u1 = 2.0f - __uint_as_float((a >> 9) | 0x3f800000u);   // (0, 1]
   const float u2 = __uint_as_float((b >> 9) | 0x3f800000u) - 1.0f;   // [0, 1)
@@ -230,6 +253,12 @@ sample_ade_fde_kernel(const float* __restrict__ Vpred, const float* __restrict__
         cx[i] = cy[i] = 0.f;
         acc[i] = fd[i] = Acc(0);
       }
+      // throughput path (fp32 distances, nothing extra to store): samples (0,1) and (2,3) of the thread advance
+      // as packed pairs, sample 4 alone -- bit-identical to the scalar loop, ~10 % fewer instructions
+      constexpr bool PACK = !EXACT && !EXTRA && E_KU == 5;
+      float2 cxp[2], cyp[2], accp[2], fdp[2];
+#pragma unroll
+      for (int q = 0; q < 2; ++q) cxp[q] = cyp[q] = accp[q] = fdp[q] = make_float2(0.f, 0.f);
 #pragma unroll 1
       for (int tp = 0; tp < T_PRED / 2; ++tp) {  // not unrolled: keeps the 84 shared-memory parameter loads from being hoisted
         float2 e2[2][E_KU];
@@ -254,8 +283,26 @@ sample_ade_fde_kernel(const float* __restrict__ Vpred, const float* __restrict__
           const int t = 2 * tp + hh;
           const float mux = par[t][0][pl], muy = par[t][1][pl], l00 = par[t][2][pl], l10 = par[t][3][pl],
                       l11 = par[t][4][pl], gx = par[t][5][pl], gy = par[t][6][pl];
+          if constexpr (PACK) {
+            const float2 ngx = bc2(-gx), ngy = bc2(-gy), ix = bc2(init.x), iy = bc2(init.y);
 #pragma unroll
-          for (int i = 0; i < E_KU; ++i) {
+            for (int q = 0; q < 2; ++q) {
+              const float2 ex = make_float2(e2[hh][2 * q].x, e2[hh][2 * q + 1].x);
+              const float2 ey = make_float2(e2[hh][2 * q].y, e2[hh][2 * q + 1].y);
+              const float2 sx = fma2(bc2(l00), ex, bc2(mux));
+              const float2 sy = fma2(bc2(l11), ey, fma2(bc2(l10), ex, bc2(muy)));
+              cxp[q] = add2(cxp[q], sx);
+              cyp[q] = add2(cyp[q], sy);
+              const float2 dx = add2(add2(cxp[q], ix), ngx);   // (cx + init.x) - gx, each rounded like the scalar path
+              const float2 dy = add2(add2(cyp[q], iy), ngy);
+              const float2 s2 = fma2(dx, dx, mul2(dy, dy));
+              const float2 d = make_float2(sqrt_approx(s2.x), sqrt_approx(s2.y));
+              accp[q] = add2(accp[q], d);
+              fdp[q] = d;
+            }
+          }
+#pragma unroll
+          for (int i = PACK ? 4 : 0; i < E_KU; ++i) {
             const float2 e = e2[hh][i];
             float sxv, syv;
             if (EXACT) {  // sample = mean + L @ eps with the separate roundings of the bmm + add of rsample
@@ -289,6 +336,13 @@ sample_ade_fde_kernel(const float* __restrict__ Vpred, const float* __restrict__
               fd[i] = d;
             }
           }
+        }
+      }
+      if constexpr (PACK) {
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          acc[2 * q] = accp[q].x, acc[2 * q + 1] = accp[q].y;
+          fd[2 * q] = fdp[q].x, fd[2 * q + 1] = fdp[q].y;
         }
       }
 #pragma unroll
