@@ -78,13 +78,23 @@ __device__ __forceinline__ float2 fma2(const float2 a, const float2 b, const flo
 }
 __device__ __forceinline__ float2 bc2(const float v) { return make_float2(v, v); }
 
-__device__ __forceinline__ float2 box_muller(uint32_t a, uint32_t b) {
-  const float u1 = 2.0f - __uint_as_float((a >> 9) | 0x3f800000u);   // (0, 1]
-  const float u2 = __uint_as_float((b >> 9) | 0x3f800000u) - 1.0f;   // [0, 1)
-  const float r = sqrt_approx(-1.3862943611198906f * __log2f(u1));   // sqrt(-2 ln u1)
-  float sn, cs;
-  __sincosf(6.283185307179586f * u2, &sn, &cs);
-  return make_float2(r * cs, r * sn);
+// The two Box-Muller transforms of one Philox output, (r.x, r.y) -> e0 and (r.z, r.w) -> e1, with their arithmetic
+// packed pairwise: u1 = 2 - f(a) in (0, 1], u2 = f(b) - 1 in [0, 1) with f(w) = as_float((w >> 9) | 0x3f800000),
+// radius sqrt(-2 ln u1) = sqrt(-1.386... * log2 u1), angle 2 pi u2, e = radius * (cos, sin).  Every operation is
+// rounded exactly as in the scalar recipe tests/philox_ref.py replays (2 - x == fma(x, -1, 2) exactly).
+__device__ __forceinline__ void box_muller2(const uint4 r, float2& e0, float2& e1) {
+  const float2 fa = make_float2(__uint_as_float((r.x >> 9) | 0x3f800000u), __uint_as_float((r.z >> 9) | 0x3f800000u));
+  const float2 fb = make_float2(__uint_as_float((r.y >> 9) | 0x3f800000u), __uint_as_float((r.w >> 9) | 0x3f800000u));
+  const float2 u1 = fma2(fa, bc2(-1.0f), bc2(2.0f));                 // (0, 1]
+  const float2 u2 = add2(fb, bc2(-1.0f));                            // [0, 1)
+  const float2 t = mul2(bc2(-1.3862943611198906f), make_float2(__log2f(u1.x), __log2f(u1.y)));
+  const float2 rr = make_float2(sqrt_approx(t.x), sqrt_approx(t.y));  // sqrt(-2 ln u1)
+  const float2 ang = mul2(bc2(6.283185307179586f), u2);
+  float sn0, cs0, sn1, cs1;
+  __sincosf(ang.x, &sn0, &cs0);
+  __sincosf(ang.y, &sn1, &cs1);
+  e0 = mul2(bc2(rr.x), make_float2(cs0, sn0));
+  e1 = mul2(bc2(rr.y), make_float2(cs1, sn1));
 }
 
 // scene of packed pedestrian p: largest s with seg_off[s] <= p
@@ -268,8 +278,7 @@ sample_ade_fde_kernel(const float* __restrict__ Vpred, const float* __restrict__
           if (PHILOX) {
             const uint4 r = Philox::run(make_uint4(static_cast<uint32_t>(k * (T_PRED / 2) + tp), 0u,
                                                    static_cast<uint32_t>(p), 0u), key);
-            e2[0][i] = box_muller(r.x, r.y);
-            e2[1][i] = box_muller(r.z, r.w);
+            box_muller2(r, e2[0][i], e2[1][i]);
           } else if (k < K) {
             const size_t ei = eb + (static_cast<size_t>(k * T_PRED + 2 * tp) * N + nl) * 2;
             e2[0][i] = *reinterpret_cast<const float2*>(eps + ei);
