@@ -12,6 +12,7 @@ ap.add_argument("--scenes", type=int, default=32768)
 ap.add_argument("--peds", type=int, default=64)
 ap.add_argument("--iters", type=int, default=5)
 ap.add_argument("--fp64", action="store_true")
+ap.add_argument("--only", default="", help="comma-separated substrings: time only the matching kernels (the others run once)")
 a = ap.parse_args()
 dev = torch.device("cuda", 0)
 S, N = a.scenes, a.peds
@@ -29,6 +30,9 @@ dp = plan.on(dev)
 ws = eng.workspace(plan)
 
 def timeit(fn, name, bytes_=None, flops=None):
+    if a.only and not any(k in name for k in a.only.split(",")):
+        fn()
+        return 0.0
     for _ in range(2): fn()
     torch.cuda.synchronize()
     ts = []

@@ -26,8 +26,8 @@ namespace sstg {
 
 namespace {
 
-constexpr int E_PEDS = 32;  // pedestrians per CTA: small CTAs (128 threads) so that 5 fit an SM and one CTA's
-                            // latency-bound prologue overlaps the sampling loops of the others
+constexpr int E_PEDS = 32;  // pedestrians per CTA: small CTAs (128 threads, 64 registers in the throughput form) so that
+                            // 8 fit an SM and one CTA's latency-bound prologue overlaps the sampling loops of the others
 constexpr int E_SUB = 4;
 constexpr int E_THREADS = E_PEDS * E_SUB;
 
@@ -53,6 +53,13 @@ struct Philox {
 __device__ __forceinline__ float sqrt_approx(float x) {
   float y;
   asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// u1 is in [2^-23, 1]: never denormal, so the .ftz form returns the same bits as __log2f without its
+// denormal-input fix-up (FSETP + FMUL + FADD per call)
+__device__ __forceinline__ float lg2_approx(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
 // packed FP32 (sm_100 FADD2 / FMUL2 / FFMA2): two IEEE fp32 operations per issue slot, each component rounded
@@ -87,7 +94,7 @@ __device__ __forceinline__ void box_muller2(const uint4 r, float2& e0, float2& e
   const float2 fb = make_float2(__uint_as_float((r.y >> 9) | 0x3f800000u), __uint_as_float((r.w >> 9) | 0x3f800000u));
   const float2 u1 = fma2(fa, bc2(-1.0f), bc2(2.0f));                 // (0, 1]
   const float2 u2 = add2(fb, bc2(-1.0f));                            // [0, 1)
-  const float2 t = mul2(bc2(-1.3862943611198906f), make_float2(__log2f(u1.x), __log2f(u1.y)));
+  const float2 t = mul2(bc2(-1.3862943611198906f), make_float2(lg2_approx(u1.x), lg2_approx(u1.y)));
   const float2 rr = make_float2(sqrt_approx(t.x), sqrt_approx(t.y));  // sqrt(-2 ln u1)
   const float2 ang = mul2(bc2(6.283185307179586f), u2);
   float sn0, cs0, sn1, cs1;
@@ -95,6 +102,28 @@ __device__ __forceinline__ void box_muller2(const uint4 r, float2& e0, float2& e
   __sincosf(ang.y, &sn1, &cs1);
   e0 = mul2(bc2(rr.x), make_float2(cs0, sn0));
   e1 = mul2(bc2(rr.y), make_float2(cs1, sn1));
+}
+
+// The same transform for the first (SECOND = false: words x, y) or second (words z, w) normal pair of TWO Philox
+// outputs at once, packed ACROSS the two draws: ex = (e.x of draw a, e.x of draw b), ey likewise -- the layout the
+// packed trajectory arithmetic consumes, so no register-pair shuffling sits between the two.  Same operations,
+// same roundings per component as box_muller2.
+template <bool SECOND>
+__device__ __forceinline__ void box_muller_pair(const uint4 ra, const uint4 rb, float2& ex, float2& ey) {
+  const uint32_t a0 = SECOND ? ra.z : ra.x, a1 = SECOND ? ra.w : ra.y;
+  const uint32_t b0 = SECOND ? rb.z : rb.x, b1 = SECOND ? rb.w : rb.y;
+  const float2 fa = make_float2(__uint_as_float((a0 >> 9) | 0x3f800000u), __uint_as_float((b0 >> 9) | 0x3f800000u));
+  const float2 fb = make_float2(__uint_as_float((a1 >> 9) | 0x3f800000u), __uint_as_float((b1 >> 9) | 0x3f800000u));
+  const float2 u1 = fma2(fa, bc2(-1.0f), bc2(2.0f));
+  const float2 u2 = add2(fb, bc2(-1.0f));
+  const float2 t = mul2(bc2(-1.3862943611198906f), make_float2(lg2_approx(u1.x), lg2_approx(u1.y)));
+  const float2 rr = make_float2(sqrt_approx(t.x), sqrt_approx(t.y));
+  const float2 ang = mul2(bc2(6.283185307179586f), u2);
+  float sna, csa, snb, csb;
+  __sincosf(ang.x, &sna, &csa);
+  __sincosf(ang.y, &snb, &csb);
+  ex = mul2(rr, make_float2(csa, csb));
+  ey = mul2(rr, make_float2(sna, snb));
 }
 
 // scene of packed pedestrian p: largest s with seg_off[s] <= p
@@ -114,7 +143,7 @@ constexpr int E_KU = 5;  // samples a thread advances together (K = 20 -> one pa
 // PHILOX : draw the noise in-kernel instead of reading eps.
 // EXTRA  : eps_out / pred_abs requested (raw_data_dict, test.py:105).
 template <bool EXACT, bool PHILOX, bool EXTRA>
-__global__ void __launch_bounds__(E_THREADS, 4)
+__global__ void __launch_bounds__(E_THREADS, (EXACT || EXTRA) ? 4 : 8)
 sample_ade_fde_kernel(const float* __restrict__ Vpred, const float* __restrict__ Vtr,
                       const float* __restrict__ last_obs, const int32_t* __restrict__ seg_off, int S, int K,
                       const float* __restrict__ eps, uint64_t seed, float* __restrict__ eps_out,
@@ -176,7 +205,10 @@ sample_ade_fde_kernel(const float* __restrict__ Vpred, const float* __restrict__
     }
   }
   __syncthreads();
-  // ---- distribution parameters per (t, pedestrian): all 15 loads of a thread are issued first
+  // ---- distribution parameters per (t, pedestrian) and the ground-truth absolute trajectory.  All global
+  // loads of the prologue -- 15 parameter loads per thread, and for the first warp the pedestrian's 24
+  // ground-truth displacements and start position -- are issued before any of the arithmetic, so that a CTA
+  // pays ONE memory latency here, not two.
   {
     constexpr int PER = T_PRED * E_PEDS / E_THREADS;  // 3
     float in[PER][5];
@@ -191,6 +223,30 @@ sample_ade_fde_kernel(const float* __restrict__ Vpred, const float* __restrict__
       const float* vp = Vpred + static_cast<size_t>(n0) * 60 + t * N + nl;  // (c, t, n) at (c*12 + t)*N + n
 #pragma unroll
       for (int c = 0; c < 5; ++c) in[u][c] = ok[u] ? vp[static_cast<size_t>(c) * 12 * N] : 0.f;
+    }
+    const bool gt_thread = tid < E_PEDS && sc_N[tid < E_PEDS ? tid : 0] > 0;
+    float rx[T_PRED], ry[T_PRED];
+    float2 gt_init = make_float2(0.f, 0.f);
+    if (gt_thread) {
+      const int N = sc_N[tid], n0 = sc_n0[tid], nl = p_base + tid - n0;
+      gt_init = reinterpret_cast<const float2*>(last_obs)[p_base + tid];
+      if (vtr_is_rel) {  // Vtr is pred_traj_rel [P,2,12]: this pedestrian's 24 floats are contiguous
+        const float4* pr = reinterpret_cast<const float4*>(Vtr + static_cast<size_t>(p_base + tid) * (2 * T_PRED));
+#pragma unroll
+        for (int i = 0; i < T_PRED / 4; ++i) {
+          const float4 a = pr[i], b = pr[T_PRED / 4 + i];
+          rx[4 * i] = a.x, rx[4 * i + 1] = a.y, rx[4 * i + 2] = a.z, rx[4 * i + 3] = a.w;
+          ry[4 * i] = b.x, ry[4 * i + 1] = b.y, ry[4 * i + 2] = b.z, ry[4 * i + 3] = b.w;
+        }
+      } else {
+        const float2* vt = reinterpret_cast<const float2*>(Vtr) + static_cast<size_t>(n0) * T_PRED + nl;
+#pragma unroll
+        for (int t = 0; t < T_PRED; ++t) {
+          const float2 v = vt[t * N];
+          rx[t] = v.x;
+          ry[t] = v.y;
+        }
+      }
     }
 #pragma unroll
     for (int u = 0; u < PER; ++u) {
@@ -210,38 +266,18 @@ sample_ade_fde_kernel(const float* __restrict__ Vpred, const float* __restrict__
       par[t][3][pl] = L10;
       par[t][4][pl] = L11;
     }
-  }
-  // ---- ground-truth absolute trajectory: sequential fp32 prefix sum, then the start position.
-  // metrics.py:69-75 adds the start in fp64 and stores fp32; fp32(fp64(a) + fp64(b)) equals the
-  // fp32 sum (double rounding through a 53 >= 2*24+2 bit format is innocuous), so __fadd_rn is bit-exact.
-  if (tid < E_PEDS && sc_N[tid] > 0) {
-    const int N = sc_N[tid], n0 = sc_n0[tid], nl = p_base + tid - n0;
-    const float2 init = reinterpret_cast<const float2*>(last_obs)[p_base + tid];
-    float rx[T_PRED], ry[T_PRED];
-    if (vtr_is_rel) {  // Vtr is pred_traj_rel [P,2,12]: this pedestrian's 24 floats are contiguous
-      const float4* pr = reinterpret_cast<const float4*>(Vtr + static_cast<size_t>(p_base + tid) * (2 * T_PRED));
-#pragma unroll
-      for (int i = 0; i < T_PRED / 4; ++i) {
-        const float4 a = pr[i], b = pr[T_PRED / 4 + i];
-        rx[4 * i] = a.x, rx[4 * i + 1] = a.y, rx[4 * i + 2] = a.z, rx[4 * i + 3] = a.w;
-        ry[4 * i] = b.x, ry[4 * i + 1] = b.y, ry[4 * i + 2] = b.z, ry[4 * i + 3] = b.w;
-      }
-    } else {
-      const float2* vt = reinterpret_cast<const float2*>(Vtr) + static_cast<size_t>(n0) * T_PRED + nl;
+    // ground-truth absolute trajectory: sequential fp32 prefix sum, then the start position.
+    // metrics.py:69-75 adds the start in fp64 and stores fp32; fp32(fp64(a) + fp64(b)) equals the
+    // fp32 sum (double rounding through a 53 >= 2*24+2 bit format is innocuous), so __fadd_rn is bit-exact.
+    if (gt_thread) {
+      float cx = 0.f, cy = 0.f;
 #pragma unroll
       for (int t = 0; t < T_PRED; ++t) {
-        const float2 v = vt[t * N];
-        rx[t] = v.x;
-        ry[t] = v.y;
+        cx = __fadd_rn(cx, rx[t]);
+        cy = __fadd_rn(cy, ry[t]);
+        par[t][5][tid] = __fadd_rn(cx, gt_init.x);
+        par[t][6][tid] = __fadd_rn(cy, gt_init.y);
       }
-    }
-    float cx = 0.f, cy = 0.f;
-#pragma unroll
-    for (int t = 0; t < T_PRED; ++t) {
-      cx = __fadd_rn(cx, rx[t]);
-      cy = __fadd_rn(cy, ry[t]);
-      par[t][5][tid] = __fadd_rn(cx, init.x);
-      par[t][6][tid] = __fadd_rn(cy, init.y);
     }
   }
   __syncthreads();
@@ -272,19 +308,33 @@ sample_ade_fde_kernel(const float* __restrict__ Vpred, const float* __restrict__
 #pragma unroll 1
       for (int tp = 0; tp < T_PRED / 2; ++tp) {  // not unrolled: keeps the 84 shared-memory parameter loads from being hoisted
         float2 e2[2][E_KU];
-#pragma unroll
-        for (int i = 0; i < E_KU; ++i) {
+        float2 exq[2][2], eyq[2][2];  // PACK && PHILOX: noise of the sample pairs (0,1), (2,3), packed across the pair
+        auto draw = [&](int i) {
           const int k = kb + E_SUB * i;
-          if (PHILOX) {
-            const uint4 r = Philox::run(make_uint4(static_cast<uint32_t>(k * (T_PRED / 2) + tp), 0u,
-                                                   static_cast<uint32_t>(p), 0u), key);
-            box_muller2(r, e2[0][i], e2[1][i]);
-          } else if (k < K) {
-            const size_t ei = eb + (static_cast<size_t>(k * T_PRED + 2 * tp) * N + nl) * 2;
-            e2[0][i] = *reinterpret_cast<const float2*>(eps + ei);
-            e2[1][i] = *reinterpret_cast<const float2*>(eps + ei + static_cast<size_t>(N) * 2);
-          } else {
-            e2[0][i] = e2[1][i] = make_float2(0.f, 0.f);
+          return Philox::run(make_uint4(static_cast<uint32_t>(k * (T_PRED / 2) + tp), 0u, static_cast<uint32_t>(p), 0u),
+                             key);
+        };
+        if constexpr (PACK && PHILOX) {
+#pragma unroll
+          for (int q = 0; q < 2; ++q) {
+            const uint4 ra = draw(2 * q), rb = draw(2 * q + 1);
+            box_muller_pair<false>(ra, rb, exq[0][q], eyq[0][q]);
+            box_muller_pair<true>(ra, rb, exq[1][q], eyq[1][q]);
+          }
+          box_muller2(draw(4), e2[0][4], e2[1][4]);
+        } else {
+#pragma unroll
+          for (int i = 0; i < E_KU; ++i) {
+            const int k = kb + E_SUB * i;
+            if (PHILOX) {
+              box_muller2(draw(i), e2[0][i], e2[1][i]);
+            } else if (k < K) {
+              const size_t ei = eb + (static_cast<size_t>(k * T_PRED + 2 * tp) * N + nl) * 2;
+              e2[0][i] = *reinterpret_cast<const float2*>(eps + ei);
+              e2[1][i] = *reinterpret_cast<const float2*>(eps + ei + static_cast<size_t>(N) * 2);
+            } else {
+              e2[0][i] = e2[1][i] = make_float2(0.f, 0.f);
+            }
           }
         }
 #pragma unroll
@@ -296,8 +346,8 @@ sample_ade_fde_kernel(const float* __restrict__ Vpred, const float* __restrict__
             const float2 ngx = bc2(-gx), ngy = bc2(-gy), ix = bc2(init.x), iy = bc2(init.y);
 #pragma unroll
             for (int q = 0; q < 2; ++q) {
-              const float2 ex = make_float2(e2[hh][2 * q].x, e2[hh][2 * q + 1].x);
-              const float2 ey = make_float2(e2[hh][2 * q].y, e2[hh][2 * q + 1].y);
+              const float2 ex = PHILOX ? exq[hh][q] : make_float2(e2[hh][2 * q].x, e2[hh][2 * q + 1].x);
+              const float2 ey = PHILOX ? eyq[hh][q] : make_float2(e2[hh][2 * q].y, e2[hh][2 * q + 1].y);
               const float2 sx = fma2(bc2(l00), ex, bc2(mux));
               const float2 sy = fma2(bc2(l11), ey, fma2(bc2(l10), ex, bc2(muy)));
               cxp[q] = add2(cxp[q], sx);

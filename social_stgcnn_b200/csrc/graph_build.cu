@@ -346,7 +346,7 @@ graph_build_fast_kernel(const float* __restrict__ rel, const int32_t* __restrict
               o.y = fmaf(-(w4[u].y * dh[u]), dk.y, 0.f);
               o.z = fmaf(-(w4[u].z * dh[u]), dk.z, 0.f);
               o.w = fmaf(-(w4[u].w * dh[u]), dk.w, 0.f);
-              *reinterpret_cast<float4*>(adst + u * stride) = o;
+              *reinterpret_cast<float4*>(adst + u * stride) = o;  // plain stores: st.global.cs (evict-first) measured 3 % slower
             }
             wsrc += 4 * stride;
             adst += 4 * stride;

@@ -144,6 +144,9 @@ stgcn_fwd_kernel(const float* __restrict__ V, const float* __restrict__ A, const
   __syncthreads();
 
   // ---- producer prologue: fill this warp's ring
+  // A is read exactly once: an L2 evict-first policy on the bulk copies keeps the stream from displacing V, the
+  // offsets and H's write-back lines (3.49 -> 3.43 ms per 131,072 scenes of 64)
+  const uint64_t l2_pol = l2_evict_first_policy();
   Cursor pc;
   cursor_open(pc, blockIdx.x, S, t, L.chunk_floats, seg_off, a_off, A);
   auto produce = [&](int stage) {
@@ -157,7 +160,7 @@ stgcn_fwd_kernel(const float* __restrict__ V, const float* __restrict__ A, const
     if (lane == 0) {
       const uint32_t bytes = static_cast<uint32_t>(e1 - b0);
       mbar_arrive_expect_tx(&full[stage], bytes);
-      bulk_g2s(ring + stage * stage_floats, reinterpret_cast<const void*>(b0), bytes, &full[stage]);
+      bulk_g2s_hint(ring + stage * stage_floats, reinterpret_cast<const void*>(b0), bytes, &full[stage], l2_pol);
     }
     pc.r0 += rows;
     if (pc.r0 >= pc.N) cursor_open(pc, pc.s + gridDim.x, S, t, L.chunk_floats, seg_off, a_off, A);
