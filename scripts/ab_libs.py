@@ -1,6 +1,6 @@
 """A/B several builds of libsstg.so in ONE process on the dense-crowd workload (CUDA events).
 
-    python scripts/ab_libs.py [--scenes 131072] [--peds 64] [--rounds 3] lib_a.so lib_b.so ...
+    python scripts/ab_libs.py [--scenes 131072] [--peds 64] [--rounds 3] lib_a.so lib_b.so@SSTG_TXP_WINO=4 ...
 
 The four inference kernels are timed for every library, interleaved over `rounds` passes (so that clock or
 thermal drift hits all builds alike); every output is compared BITWISE with the first library's.
@@ -37,7 +37,20 @@ obs_rel, pred_rel, last = obs_rel.to(dev), pred_rel.to(dev), last.to(dev)
 w = np.load(os.path.join(os.path.dirname(__file__), "..", "tests", "golden", "weights.npz"))
 
 
-def use(path):
+_env_set = []
+
+
+def use(spec):
+    """spec = path[@KEY=VAL[,KEY=VAL...]]: the library to load and the tuning knobs (read by the library with getenv
+    at every launch) to set while it is in use."""
+    path, _, env = spec.partition("@")
+    for k in _env_set:
+        os.environ.pop(k, None)
+    _env_set.clear()
+    for kv in filter(None, env.split(",")):
+        k, v = kv.split("=")
+        os.environ[k] = v
+        _env_set.append(k)
     L._lib = None
     L.LIB_PATH = os.path.abspath(path)
     L.load()
@@ -83,4 +96,4 @@ for rnd in range(a.rounds):
                 times[lib][name].append(e0.elapsed_time(e1))
 for lib in a.libs:
     row = "  ".join(f"{name} {np.median(v):7.3f}" for name, v in times[lib].items() if v)
-    print(f"{os.path.basename(lib):24s} {row}", flush=True)
+    print(f"{os.path.basename(lib):40s} {row}", flush=True)

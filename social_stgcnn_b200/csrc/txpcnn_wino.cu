@@ -195,7 +195,9 @@ txpcnn_wino_kernel(const float* __restrict__ Hin, const int32_t* __restrict__ se
         const float* Ul = (CONSTW ? c_U + GRP * COT * 4 : sm.U + co0 * 4) + (l == 0 ? 0 : W_U0 + (l - 1) * W_UL);
         const int CI = (l == 0) ? 8 : 12;
         constexpr int STEPS = 3 * COT;
-        constexpr int NPF = (CONSTW && STEPS % WINO_NPF_CONST == 0) ? WINO_NPF_CONST : WINO_NPF;
+        constexpr int NPF = !CONSTW ? WINO_NPF
+                            : (STEPS % WINO_NPF_CONST == 0) ? WINO_NPF_CONST
+                            : (STEPS % 6 == 0) ? 6 : WINO_NPF;
         static_assert(STEPS % NPF == 0, "the filter ring must keep its phase from one input channel to the next");
         const float* a = act + sc0 - 1;  // even offset: aligned float2 loads
         float2 d01[5], d23[5];
