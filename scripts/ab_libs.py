@@ -69,6 +69,16 @@ steps = [
                                         min_ade=ws["min_ade"], min_fde=ws["min_fde"]),
      lambda: torch.cat([ws["min_ade"], ws["min_fde"]])),
 ]
+# the same kernel with INJECTED noise (the <EXACT=0, PHILOX=0> instantiation) on the first scenes of the batch
+S2 = min(S, 4096)
+P2 = S2 * N
+dp2 = sstg.ScenePlan(np.full(S2, N, np.int32)).on(dev)
+eps2 = torch.randn(P2 * 20 * 24, generator=torch.Generator(device="cpu").manual_seed(1)).to(dev)
+ade2 = torch.empty(P2, dtype=torch.float64, device=dev)
+fde2 = torch.empty(P2, dtype=torch.float64, device=dev)
+steps.append(("sample_eps", lambda: E.sample_ade_fde(dp2, ws["V_pred"][: P2 * 60], pred_rel[:P2], last[:P2], 20, eps=eps2,
+                                                    fp64_dist=False, vtr_is_rel=True, min_ade=ade2, min_fde=fde2),
+              lambda: torch.cat([ade2, fde2])))
 ref = {}
 times = {lib: {name: [] for name, _, _ in steps} for lib in a.libs}
 for rnd in range(a.rounds):

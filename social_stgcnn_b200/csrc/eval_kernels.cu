@@ -137,6 +137,14 @@ __device__ __forceinline__ int find_scene(const int32_t* __restrict__ seg_off, i
 }
 
 constexpr int E_KU = 5;  // samples a thread advances together (K = 20 -> one pass of 4 x 5)
+// Of the two sample pairs (0,1), (2,3) of a thread, how many advance as PACKED FP32 pairs in the throughput form (the rest,
+// and sample 4, as scalar chains; same roundings either way).  ncu shows the heavy half of the FMA pipe as the busiest unit
+// (74 %: Philox's IMAD.WIDE plus the packed FP32), but un-packing does not relieve it: measured 2.13 / 2.18 / 2.24 ms per
+// 65,536 scenes x 64 for 2 / 1 / 0 packed pairs (profiles/r1an_ab_traj_packed.txt).  A/B knob: -DSSTG_E_TRAJ_PACKED=0|1|2.
+#ifndef SSTG_E_TRAJ_PACKED
+#define SSTG_E_TRAJ_PACKED 2
+#endif
+constexpr int E_TRAJ_PACKED = SSTG_E_TRAJ_PACKED;
 
 // EXACT  : the reference's rounding points (separately rounded mean + L eps, fp64 sqrt and
 //          fp64 sequential sum of the 12 distances, metrics.py:33-34,50); otherwise fp32 with FMA.
@@ -348,16 +356,30 @@ sample_ade_fde_kernel(const float* __restrict__ Vpred, const float* __restrict__
             for (int q = 0; q < 2; ++q) {
               const float2 ex = PHILOX ? exq[hh][q] : make_float2(e2[hh][2 * q].x, e2[hh][2 * q + 1].x);
               const float2 ey = PHILOX ? eyq[hh][q] : make_float2(e2[hh][2 * q].y, e2[hh][2 * q + 1].y);
-              const float2 sx = fma2(bc2(l00), ex, bc2(mux));
-              const float2 sy = fma2(bc2(l11), ey, fma2(bc2(l10), ex, bc2(muy)));
-              cxp[q] = add2(cxp[q], sx);
-              cyp[q] = add2(cyp[q], sy);
-              const float2 dx = add2(add2(cxp[q], ix), ngx);   // (cx + init.x) - gx, each rounded like the scalar path
-              const float2 dy = add2(add2(cyp[q], iy), ngy);
-              const float2 s2 = fma2(dx, dx, mul2(dy, dy));
-              const float2 d = make_float2(sqrt_approx(s2.x), sqrt_approx(s2.y));
-              accp[q] = add2(accp[q], d);
-              fdp[q] = d;
+              if (q < E_TRAJ_PACKED) {
+                const float2 sx = fma2(bc2(l00), ex, bc2(mux));
+                const float2 sy = fma2(bc2(l11), ey, fma2(bc2(l10), ex, bc2(muy)));
+                cxp[q] = add2(cxp[q], sx);
+                cyp[q] = add2(cyp[q], sy);
+                const float2 dx = add2(add2(cxp[q], ix), ngx);   // (cx + init.x) - gx, each rounded like the scalar path
+                const float2 dy = add2(add2(cyp[q], iy), ngy);
+                const float2 s2 = fma2(dx, dx, mul2(dy, dy));
+                const float2 d = make_float2(sqrt_approx(s2.x), sqrt_approx(s2.y));
+                accp[q] = add2(accp[q], d);
+                fdp[q] = d;
+              } else {  // the same pair as two scalar chains (light half of the FMA pipe; see E_TRAJ_PACKED)
+                cxp[q].x = __fadd_rn(cxp[q].x, fmaf(l00, ex.x, mux));
+                cxp[q].y = __fadd_rn(cxp[q].y, fmaf(l00, ex.y, mux));
+                cyp[q].x = __fadd_rn(cyp[q].x, fmaf(l11, ey.x, fmaf(l10, ex.x, muy)));
+                cyp[q].y = __fadd_rn(cyp[q].y, fmaf(l11, ey.y, fmaf(l10, ex.y, muy)));
+                const float dx0 = __fsub_rn(__fadd_rn(cxp[q].x, init.x), gx), dx1 = __fsub_rn(__fadd_rn(cxp[q].y, init.x), gx);
+                const float dy0 = __fsub_rn(__fadd_rn(cyp[q].x, init.y), gy), dy1 = __fsub_rn(__fadd_rn(cyp[q].y, init.y), gy);
+                const float2 d = make_float2(sqrt_approx(fmaf(dx0, dx0, __fmul_rn(dy0, dy0))),
+                                             sqrt_approx(fmaf(dx1, dx1, __fmul_rn(dy1, dy1))));
+                accp[q].x = __fadd_rn(accp[q].x, d.x);
+                accp[q].y = __fadd_rn(accp[q].y, d.y);
+                fdp[q] = d;
+              }
             }
           }
 #pragma unroll
