@@ -53,16 +53,27 @@ constexpr int W_WP_MAX = 200;                  // widest tile row: 128 columns +
 __constant__ float c_U[W_UTOTAL + 4 * 32];  // transformed filters of the launch in flight (CONSTW variant);
                                             // the tail pads the prefetch ring's run past the last filter
 
-template <bool CONSTW>
-struct WSmemT {
-  float U[CONSTW ? 4 : W_UTOTAL];
-  float bias[5][12];
-  float slope[4];
+// scene placement of one tile inside the shared activation tile
+struct WTab {
   int s_first[SSTG_XTILE_MAX_SCENES + 1];  // first (odd) shared-memory column of each scene
   int s_pair[SSTG_XTILE_MAX_SCENES + 1];   // first pair index of each scene
   int s_n[SSTG_XTILE_MAX_SCENES];          // pedestrians of each scene
   int s_sb[SSTG_XTILE_MAX_SCENES];         // first tile column of each scene
   int n_pairs, used_cols;
+};
+struct WTabPF : WTab {  // the prefetch variant keeps the tile's extent next to its table (computed a tile ahead)
+  int nsc, p_lo, cols;
+};
+__device__ __forceinline__ int tab_p_lo(const WTab&) { return 0; }
+__device__ __forceinline__ int tab_p_lo(const WTabPF& t) { return t.p_lo; }
+
+template <bool CONSTW, bool PF>
+struct WSmemT {
+  float U[CONSTW ? 4 : W_UTOTAL];
+  float bias[5][12];
+  float slope[4];
+  // PF: the table of the tile being computed and of the tile being prefetched
+  typename std::conditional<PF, WTabPF, WTab>::type tab[PF ? 2 : 1];
 };
 
 // W_WP (even, <= W_WP_MAX) is the row stride of the activation tile: the launcher sizes it for the widest
@@ -90,7 +101,12 @@ __global__ void wino_filter_kernel(const float* __restrict__ params, float* __re
   if (i < W_UTOTAL / 4) reinterpret_cast<float4*>(U)[i] = wino_filter(params, i);
 }
 
-template <int NSPLIT, bool CONSTW>
+// PF = true (SSTG_TXP_PREFETCH=1, not the default yet): the 40 input rows of the NEXT tile are fetched into a separate
+// staging tile while layers 1..4 of the current tile run, so the per-tile prologue -- scene placement, zeroing and one
+// global-memory round trip behind three barriers: 12.5 % of the stall samples of the plain kernel
+// (profiles/r1am_ncu_full_summary.csv) although only 2 % of its instructions -- leaves the critical path.  Layer 0 then reads
+// the staging tile, everything else is unchanged (same arithmetic, same order: bit-identical results).
+template <int NSPLIT, bool CONSTW, bool PF>
 __global__ void __launch_bounds__(NSPLIT * W_PAIRS, 2)
 txpcnn_wino_kernel(const float* __restrict__ Hin, const int32_t* __restrict__ seg_off,
                    const int32_t* __restrict__ tile_off, int n_tiles, const float* __restrict__ params,
@@ -98,9 +114,10 @@ txpcnn_wino_kernel(const float* __restrict__ Hin, const int32_t* __restrict__ se
   constexpr int COT = 12 / NSPLIT;
   constexpr int THREADS = NSPLIT * W_PAIRS;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  using WSmem = WSmemT<CONSTW>;
+  using WSmem = WSmemT<CONSTW, PF>;
   WSmem& sm = *reinterpret_cast<WSmem*>(smem_raw);
   float* act = reinterpret_cast<float*>(smem_raw + ((sizeof(WSmem) + 15) & ~size_t(15)));  // [60][W_WP]
+  float* stage = act + (PF ? X_ROWS * W_WP : 0);                                           // PF: [40][W_WP] input of the tile
   const int tid = threadIdx.x;
   const int grp = tid / W_PAIRS;  // output-channel group (warp-uniform)
   const int pt = tid - grp * W_PAIRS;
@@ -117,67 +134,131 @@ txpcnn_wino_kernel(const float* __restrict__ Hin, const int32_t* __restrict__ se
   }
   if (tid < 4) sm.slope[tid] = params[P_PRELUS + tid];
 
-  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+  // ---- helpers of the prefetch variant
+  // scene placement of tile `tile` (one thread): every scene starts at an odd column
+  auto place = [&](int tile, WTabPF& tb) {
     const int s_lo = tile_off[tile], s_hi = tile_off[tile + 1];
     const int nsc = s_hi - s_lo;
     const int p_lo = seg_off[s_lo];
-    const int cols = seg_off[s_hi] - p_lo;
-    __syncthreads();  // previous tile done; U visible
-    if (tid == 0) {   // scene placement: every scene starts at an odd column
-      int c = 1, pr = 0;
-      for (int j = 0; j < nsc; ++j) {
-        const int sb = seg_off[s_lo + j] - p_lo, n = seg_off[s_lo + j + 1] - p_lo - sb;
-        sm.s_first[j] = c;
-        sm.s_pair[j] = pr;
-        sm.s_n[j] = n;
-        sm.s_sb[j] = sb;
-        pr += (n + 1) >> 1;
-        c += n + 1;        // one separator ...
-        c += (~c) & 1;     // ... or two, so that the next scene starts odd again
-      }
-      sm.s_first[nsc] = c;  // one past the last separator pair
-      sm.s_pair[nsc] = pr;
-      sm.n_pairs = pr;
-      sm.used_cols = c + 1;
+    int c = 1, pr = 0;
+    for (int j = 0; j < nsc; ++j) {
+      const int sb = seg_off[s_lo + j] - p_lo, n = seg_off[s_lo + j + 1] - p_lo - sb;
+      tb.s_first[j] = c;
+      tb.s_pair[j] = pr;
+      tb.s_n[j] = n;
+      tb.s_sb[j] = sb;
+      pr += (n + 1) >> 1;
+      c += n + 1;
+      c += (~c) & 1;
     }
-    __syncthreads();
-    // ---- zero column 0 and the two columns behind every scene (the 1- or 2-column gap; when the gap
-    // is one column the second store hits the next scene's first column, which the loads below rewrite)
-    for (int i = tid; i < (2 * nsc + 1) * X_ROWS; i += THREADS) {
-      const int row = i % X_ROWS, k = i / X_ROWS;
-      const int col = (k == 0) ? 0 : sm.s_first[(k - 1) >> 1] + sm.s_n[(k - 1) >> 1] + ((k - 1) & 1);
-      if (col < W_WP) act[row * W_WP + col] = 0.f;
+    tb.s_first[nsc] = c;
+    tb.s_pair[nsc] = pr;
+    tb.n_pairs = pr;
+    tb.used_cols = c + 1;
+    tb.nsc = nsc;
+    tb.p_lo = p_lo;
+    tb.cols = seg_off[s_hi] - p_lo;
+  };
+  // zero column 0 and the two columns behind every scene in `rows` rows of `buf`
+  auto zero_gaps = [&](const WTabPF& tb, float* buf, int rows) {
+    for (int i = tid; i < (2 * tb.nsc + 1) * rows; i += THREADS) {
+      const int row = i % rows, k = i / rows;
+      const int col = (k == 0) ? 0 : tb.s_first[(k - 1) >> 1] + tb.s_n[(k - 1) >> 1] + ((k - 1) & 1);
+      if (col < W_WP) buf[row * W_WP + col] = 0.f;
     }
-    __syncthreads();
-    // ---- 40 input rows of every scene (cp.async, coalesced along the pedestrian axis)
-    {
-      const float* Hb = Hin + static_cast<size_t>(p_lo) * 40;
-      for (int q = tid & 127; q < cols; q += 128) {
-        int j = 0;
-        while (j + 1 < nsc && sm.s_sb[j + 1] <= q) ++j;
-        const int n = q - sm.s_sb[j], ns = sm.s_n[j];
-        const float* src = Hb + sm.s_sb[j] * 40 + n;
-        float* dst = act + sm.s_first[j] + n;
-        for (int row = (THREADS % 128 == 0) ? (tid >> 7) : 0; row < 40; row += (THREADS % 128 == 0) ? THREADS / 128 : 1)
-          if (THREADS % 128 == 0 || tid < 128) cp_async4(dst + row * W_WP, src + row * ns);
-      }
+  };
+  // issue the cp.async loads of the 40 input rows of every scene of the tile into `buf` (no wait)
+  auto load_rows = [&](const WTabPF& tb, float* buf) {
+    const float* Hb = Hin + static_cast<size_t>(tb.p_lo) * 40;
+    for (int q = tid & 127; q < tb.cols; q += 128) {
+      int j = 0;
+      while (j + 1 < tb.nsc && tb.s_sb[j + 1] <= q) ++j;
+      const int n = q - tb.s_sb[j], ns = tb.s_n[j];
+      const float* src = Hb + tb.s_sb[j] * 40 + n;
+      float* dst = buf + tb.s_first[j] + n;
+      for (int row = (THREADS % 128 == 0) ? (tid >> 7) : 0; row < 40; row += (THREADS % 128 == 0) ? THREADS / 128 : 1)
+        if (THREADS % 128 == 0 || tid < 128) cp_async4(dst + row * W_WP, src + row * ns);
+    }
+  };
+
+  int cur = 0;  // PF: index of the current tile's table
+  if constexpr (PF) {
+    if (static_cast<int>(blockIdx.x) < n_tiles) {  // the CTA's first tile: fetched in the open
+      if (tid == 0) place(blockIdx.x, sm.tab[0]);
+      __syncthreads();
+      zero_gaps(sm.tab[0], stage, 40);
+      __syncthreads();
+      load_rows(sm.tab[0], stage);
+    }
+  }
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    auto& tb = sm.tab[PF ? cur : 0];
+    const int s_lo = PF ? 0 : tile_off[tile], s_hi = PF ? 0 : tile_off[tile + 1];
+    const int nsc = s_hi - s_lo;
+    const int p_lo = PF ? tab_p_lo(tb) : seg_off[s_lo];
+    const int cols = PF ? 0 : seg_off[s_hi] - p_lo;
+    if constexpr (PF) {
       cp_async_wait_all();
+      __syncthreads();  // previous tile done; this tile's table and staging rows (prefetched) visible
+      zero_gaps(tb, act, X_ROWS);  // ordered before the first stores into `act` by layer 0's barrier
+    } else {
+      __syncthreads();  // previous tile done; U visible
+      if (tid == 0) {   // scene placement: every scene starts at an odd column
+        int c = 1, pr = 0;
+        for (int j = 0; j < nsc; ++j) {
+          const int sb = seg_off[s_lo + j] - p_lo, n = seg_off[s_lo + j + 1] - p_lo - sb;
+          tb.s_first[j] = c;
+          tb.s_pair[j] = pr;
+          tb.s_n[j] = n;
+          tb.s_sb[j] = sb;
+          pr += (n + 1) >> 1;
+          c += n + 1;        // one separator ...
+          c += (~c) & 1;     // ... or two, so that the next scene starts odd again
+        }
+        tb.s_first[nsc] = c;  // one past the last separator pair
+        tb.s_pair[nsc] = pr;
+        tb.n_pairs = pr;
+        tb.used_cols = c + 1;
+      }
+      __syncthreads();
+      // ---- zero column 0 and the two columns behind every scene (the 1- or 2-column gap; when the gap
+      // is one column the second store hits the next scene's first column, which the loads below rewrite)
+      for (int i = tid; i < (2 * nsc + 1) * X_ROWS; i += THREADS) {
+        const int row = i % X_ROWS, k = i / X_ROWS;
+        const int col = (k == 0) ? 0 : tb.s_first[(k - 1) >> 1] + tb.s_n[(k - 1) >> 1] + ((k - 1) & 1);
+        if (col < W_WP) act[row * W_WP + col] = 0.f;
+      }
+      __syncthreads();
+      // ---- 40 input rows of every scene (cp.async, coalesced along the pedestrian axis)
+      {
+        const float* Hb = Hin + static_cast<size_t>(p_lo) * 40;
+        for (int q = tid & 127; q < cols; q += 128) {
+          int j = 0;
+          while (j + 1 < nsc && tb.s_sb[j + 1] <= q) ++j;
+          const int n = q - tb.s_sb[j], ns = tb.s_n[j];
+          const float* src = Hb + tb.s_sb[j] * 40 + n;
+          float* dst = act + tb.s_first[j] + n;
+          for (int row = (THREADS % 128 == 0) ? (tid >> 7) : 0; row < 40; row += (THREADS % 128 == 0) ? THREADS / 128 : 1)
+            if (THREADS % 128 == 0 || tid < 128) cp_async4(dst + row * W_WP, src + row * ns);
+        }
+        cp_async_wait_all();
+      }
+      __syncthreads();
     }
-    __syncthreads();
 
     // ---- this thread's pair
-    const bool on = pt < sm.n_pairs;
+    const bool on = pt < tb.n_pairs;
     int sc0 = 1, pn = 1;
     bool v1 = false;
     long long gO = 0;
     if (on) {
       int j = 0;
-      while (sm.s_pair[j + 1] <= pt) ++j;
-      const int n = 2 * (pt - sm.s_pair[j]);
-      sc0 = sm.s_first[j] + n;
-      pn = sm.s_n[j];
+      while (tb.s_pair[j + 1] <= pt) ++j;
+      const int n = 2 * (pt - tb.s_pair[j]);
+      sc0 = tb.s_first[j] + n;
+      pn = tb.s_n[j];
       v1 = n + 1 < pn;
-      gO = static_cast<long long>(p_lo + sm.s_sb[j]) * 60 + n;
+      gO = static_cast<long long>(p_lo + tb.s_sb[j]) * 60 + n;
     }
 
 #pragma unroll 1
@@ -199,7 +280,7 @@ txpcnn_wino_kernel(const float* __restrict__ Hin, const int32_t* __restrict__ se
                             : (STEPS % WINO_NPF_CONST == 0) ? WINO_NPF_CONST
                             : (STEPS % 6 == 0) ? 6 : WINO_NPF;
         static_assert(STEPS % NPF == 0, "the filter ring must keep its phase from one input channel to the next");
-        const float* a = act + sc0 - 1;  // even offset: aligned float2 loads
+        const float* a = ((PF && l == 0) ? stage : act) + sc0 - 1;  // even offset: aligned float2 loads
         float2 d01[5], d23[5];
 #pragma unroll
         for (int h = 0; h < 5; ++h) {
@@ -280,7 +361,14 @@ txpcnn_wino_kernel(const float* __restrict__ Hin, const int32_t* __restrict__ se
         }
       }
       if (l < 4) {
+        if constexpr (PF) {  // the next tile's placement, published by the barrier below
+          if (l == 0 && tid == 0 && tile + static_cast<int>(gridDim.x) < n_tiles)
+            place(tile + static_cast<int>(gridDim.x), sm.tab[cur ^ 1]);
+        }
         __syncthreads();  // everyone has read the old activations
+        if constexpr (PF) {  // layer 0 was the last reader of the staging tile
+          if (l == 0 && tile + static_cast<int>(gridDim.x) < n_tiles) zero_gaps(sm.tab[cur ^ 1], stage, 40);
+        }
         if (on) {
 #pragma unroll
           for (int c = 0; c < COT; ++c)
@@ -292,6 +380,9 @@ txpcnn_wino_kernel(const float* __restrict__ Hin, const int32_t* __restrict__ se
             }
         }
         __syncthreads();
+        if constexpr (PF) {  // in flight during layers 1..4; awaited at the top of the next tile
+          if (l == 0 && tile + static_cast<int>(gridDim.x) < n_tiles) load_rows(sm.tab[cur ^ 1], stage);
+        }
       } else if (on) {
         float* o = out + gO;
 #pragma unroll
@@ -304,14 +395,15 @@ txpcnn_wino_kernel(const float* __restrict__ Hin, const int32_t* __restrict__ se
           }
       }
     }
+    if constexpr (PF) cur ^= 1;
   }
 }
 
-template <int NSPLIT, bool CONSTW>
+template <int NSPLIT, bool CONSTW, bool PF = false>
 int launch_wino_v(const float* H, const int32_t* seg_off, const int32_t* tile_off, int n_tiles, const float* params,
                   float* out, int W_WP, int grid_cap, cudaStream_t st) {
-  const size_t smem = ((sizeof(WSmemT<CONSTW>) + 15) & ~size_t(15)) + sizeof(float) * X_ROWS * W_WP;
-  auto kern = txpcnn_wino_kernel<NSPLIT, CONSTW>;
+  const size_t smem = ((sizeof(WSmemT<CONSTW, PF>) + 15) & ~size_t(15)) + sizeof(float) * (X_ROWS + (PF ? 40 : 0)) * W_WP;
+  auto kern = txpcnn_wino_kernel<NSPLIT, CONSTW, PF>;
   SSTG_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)),
                 "txpcnn_wino smem attr");
   const int grid = n_tiles < grid_cap ? n_tiles : grid_cap;
@@ -333,6 +425,12 @@ bool wino_const_allowed() {
   const char* e = getenv("SSTG_TXP_FILTERS");
   return !(e && e[0] == 's');
 }
+// SSTG_TXP_PREFETCH = 1: the next-tile prefetch variant of the 2-group constant-bank kernel (A/B knob; off by default
+// until it has been measured)
+bool wino_prefetch() {
+  const char* e = getenv("SSTG_TXP_PREFETCH");
+  return e && e[0] == '1';
+}
 
 template <int NSPLIT>
 int launch_wino(const float* H, const int32_t* seg_off, const int32_t* tile_off, int n_tiles, const float* params,
@@ -343,8 +441,13 @@ int launch_wino(const float* H, const int32_t* seg_off, const int32_t* tile_off,
   const int grid_cap = 2 * sms;  // 255 registers x 128 threads: two CTAs per SM
   // the constant-bank variant pays a ~6 us refresh per launch: worth it once the persistent grid is full
   // (then n_tiles * 60 floats of `out` also exceed the 8,064-float staging area by far)
-  if (n_tiles >= grid_cap && wino_const_allowed())
+  if (n_tiles >= grid_cap && wino_const_allowed()) {
+    if constexpr (NSPLIT == 2) {
+      if (wino_prefetch())
+        return launch_wino_v<NSPLIT, true, true>(H, seg_off, tile_off, n_tiles, params, out, W_WP, grid_cap, st);
+    }
     return launch_wino_v<NSPLIT, true>(H, seg_off, tile_off, n_tiles, params, out, W_WP, grid_cap, st);
+  }
   return launch_wino_v<NSPLIT, false>(H, seg_off, tile_off, n_tiles, params, out, W_WP, grid_cap, st);
 }
 
