@@ -126,7 +126,9 @@ int sstg_stgcn_forward_fused(const float* rel, const int32_t* seg_off, int32_t S
  * kernel reads its transformed filters from a per-device __constant__ bank that this call refreshes in
  * stream order (the head of `out` serves as staging before the kernel overwrites it).  Calls with DIFFERENT
  * `params` must therefore not be in flight on two streams of one device at the same time; calls with the
- * same weights may.  Environment SSTG_TXP_FILTERS=smem selects the variant without the bank. */
+ * same weights may.  Environment SSTG_TXP_FILTERS=smem selects the variant without the bank;
+ * SSTG_TXP_PREFETCH=1 an experimental variant that fetches the next tile's input during the current tile
+ * (same results; not the default). */
 int sstg_txpcnn_forward(const float* H, const int32_t* seg_off, const int32_t* tile_off,
                         int32_t n_tiles, int32_t max_n, int32_t tile_cols, const float* params,
                         float* out, void* stream);
