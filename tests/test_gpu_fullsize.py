@@ -276,3 +276,28 @@ def test_winograd_constant_bank_filters_equal_shared_memory_filters(golden, dev)
     torch.cuda.synchronize()
     for got, ck in zip(seq, ("eth", "zara1", "eth", "zara1")):
         assert torch.equal(got, outs[ck][1]), ck
+
+
+@pytest.mark.skipif(os.environ.get("SSTG_TEST_EXPERIMENTAL") != "1",
+                    reason="SSTG_TXP_PREFETCH is an unmeasured A/B variant: run with SSTG_TEST_EXPERIMENTAL=1 (under a timeout)")
+def test_winograd_next_tile_prefetch_variant_is_bit_identical(golden, dev):
+    """SSTG_TXP_PREFETCH=1 fetches the next tile's 40 input rows into a staging tile while the current tile's
+    layers 1..4 run.  Same arithmetic in the same order: bit-identical outputs, for dense tiles (2 x 64), ragged
+    tiles (many small scenes per tile, odd and even pedestrian counts) and a grid with a ragged last wave."""
+    import social_stgcnn_b200 as sstg
+    rng = np.random.default_rng(13)
+    for n in (np.full(4096, 64), np.concatenate([np.full(600, 64), rng.integers(2, 58, 4000)]),
+              rng.integers(2, 9, 40000), np.concatenate([rng.integers(100, 129, 300), rng.integers(2, 58, 3000)])):
+        plan = sstg.ScenePlan(n.astype(np.int32))
+        assert plan.n_tiles >= 2 * 148                      # the constant-bank variant is selected
+        dp = plan.on(dev)
+        H = torch.from_numpy(rng.standard_normal(plan.P * 40).astype(np.float32)).to(dev)
+        prm = torch.from_numpy(golden.params("eth")[0]).to(dev)
+        a = sstg.txpcnn_forward(dp, H, prm).clone()
+        os.environ["SSTG_TXP_PREFETCH"] = "1"
+        try:
+            b = sstg.txpcnn_forward(dp, H, prm).clone()
+        finally:
+            os.environ.pop("SSTG_TXP_PREFETCH", None)
+        torch.cuda.synchronize()
+        assert torch.equal(a, b), (int(n.min()), int(n.max()), len(n))
