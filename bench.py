@@ -697,7 +697,11 @@ def run_ours(args):
                             "identical_to_fp32_interface": compact_identical,
                             "how": "same pipeline fed the fixed-point host format (int32 start + int16 steps in units "
                                    "of 1e-4, sstg_decode_tracks rebuilds the fp32 tensors bit for bit on the device)"},
-            "gpu_launches": 4 * args.steps,
+            # per step: graph, st_gcn, TXP-CNN (Winograd), sampling + the 8-CTA filter-transform kernel that refreshes
+            # the Winograd constant bank before every TXP-CNN launch (plus one 32 KB device-to-device copy, not a kernel)
+            "gpu_launches": (4 + int(plan.n_tiles >= 2 * torch.cuda.get_device_properties(dev).multi_processor_count
+                                     and os.environ.get("SSTG_TXP_FILTERS", "")[:1] != "s"
+                                     and os.environ.get("SSTG_TXP_WINO", "2")[:1] != "0")) * args.steps,
             "train": train,
             "graph_construction": graph_leg,
             "ragged_inference": ragged_leg,
