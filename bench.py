@@ -69,6 +69,17 @@ def workload_name(scenes_per_gpu):
             f"the default shard), obs 8 -> pred 12, K={K_SAMPLES} Philox samples, eth checkpoint weights")
 
 
+def bench_config(scenes_per_gpu, world):
+    """`config` of the JSON line -- built by ONE function for both arms, so that the reference arm reports
+    exactly the configuration of ours (what differs between the arms, e.g. the bounded CPU sample of the
+    reference arm, is reported next to it, not inside it)."""
+    a_gb = 32.0 * N_PEDS * N_PEDS * scenes_per_gpu / 1e9
+    return {"workload": workload_name(scenes_per_gpu), "scenes_per_gpu": scenes_per_gpu, "peds_per_scene": N_PEDS,
+            "ksteps": K_SAMPLES, "graph_mode": "fp32",
+            "l2_policy": "inputs larger than L2 (A is %.1f GB per step)" % a_gb,
+            "parallelism": f"scene-sharded x{world}, no data-path collective"}
+
+
 def load_weights():
     w = np.load(os.path.join(ROOT, "tests", "golden", "weights.npz"))
     return w["eth.params"], w["eth.bn"]
@@ -194,12 +205,11 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / max(1, args.steps), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(args.scenes_per_gpu), "scenes_per_gpu": args.scenes_per_gpu,
-                   "peds_per_scene": N_PEDS, "ksteps": K_SAMPLES,
-                   "sample_per_step": f"{per_step} scenes of this workload per step (bounded CPU sample)"},
+        "config": bench_config(args.scenes_per_gpu, args.gpus),
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{done} scenes in {dt:.1f}s, oracle port (vectorised numpy graph build + torch "
-                                   f"CPU fp32 forward + numpy sampling), one process per core"},
+                         "sample": f"{per_step} scenes of this workload per step (bounded CPU sample): {done} scenes "
+                                   f"in {dt:.1f}s, oracle port (vectorised numpy graph build + torch CPU fp32 forward "
+                                   f"+ numpy sampling), one process per core"},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -668,11 +678,8 @@ def run_ours(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_name(S),
-                       "scenes_per_gpu": S, "peds_per_scene": N, "ksteps": K_SAMPLES, "graph_mode": "fp32",
-                       "l2_policy": "inputs larger than L2 (A is %.1f GB per step)" % (plan.a_floats * 4 / 1e9),
-                       "parallelism": f"scene-sharded x{world}, no data-path collective",
-                       "numa_node_rank0": numa_node},
+            "config": bench_config(S, world),
+            "host": {"numa_node_rank0": numa_node, "cpus": os.cpu_count()},
             "roofline": {"kernel": "stgcn_fwd_kernel", "bound": "hbm", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak,
                          "traffic": (tr["dram_bytes"] * S / tr["scenes"] if (tr := profiled_traffic()) else None),

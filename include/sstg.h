@@ -267,7 +267,12 @@ int sstg_train_step(const float* obs_rel, const float* pred_rel, const int32_t* 
  *   scene_lo, s_local   its scene range inside the group of s_all scenes; seg_off_all [s_all+1] (device)
  *   grad_out [7563], loss_out [1] (may be NULL), stats_out [s_all,30]: the reduced group quantities
  *   status [1] int32    device word, 0 on success; 1+r if source r had not delivered within timeout_ns
- *                       (0 = 5 s): then nothing is applied -- the kernel never spins unbounded */
+ *                       (0 = 30 s): then nothing is applied -- the kernel never spins unbounded.  The word is
+ *                       sticky: while it is non-zero this rank's calls neither push nor apply, so its peers
+ *                       time out as well and no replica trains on (the caller clears it to recover).
+ * sstg_peer_exchange_apply_local: the same exchange for a process that holds n_local ranks of the group on
+ * ONE device (single-GPU test harness): their CTAs wait on one another, so they run as ONE cooperative
+ * launch instead of n_local launches that are not guaranteed to be co-resident. */
 #define SSTG_MAX_RANKS 8
 #define SSTG_PEER_HANDLE_BYTES 64
 int64_t sstg_peer_mailbox_bytes(int32_t world, int32_t max_scenes);
@@ -275,6 +280,22 @@ int sstg_peer_alloc(int64_t bytes, void** ptr, unsigned char* handle);
 int sstg_peer_open(const unsigned char* handle, void** ptr);
 int sstg_peer_close(void* ptr);
 int sstg_peer_free(void* ptr);
+typedef struct sstg_peer_rank {
+  int32_t rank, scene_lo, s_local, reserved;
+  const float* grad_local;
+  const float* loss_local;
+  const float* stats_local;
+  const int32_t* seg_off_all;
+  float* params;
+  float* bn;
+  float* grad_out;
+  float* loss_out;
+  float* stats_out;
+  int32_t* status;
+} sstg_peer_rank;
+int sstg_peer_exchange_apply_local(void* const* mailboxes, int32_t world, const sstg_peer_rank* ranks,
+                                   int32_t n_local, uint32_t epoch, int32_t max_scenes, int32_t s_all, float lr,
+                                   float clip_norm, double bn_momentum, uint64_t timeout_ns, void* stream);
 int sstg_peer_exchange_apply(void* const* mailboxes, int32_t world, int32_t rank, uint32_t epoch,
                              int32_t max_scenes, const float* grad_local, const float* loss_local,
                              const float* stats_local, int32_t scene_lo, int32_t s_local,

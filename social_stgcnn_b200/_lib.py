@@ -13,7 +13,7 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("SSTG_LIB") or os.path.join(_PKG, "libsstg.so")   # SSTG_LIB: A/B a differently built library
 
 T_OBS, T_PRED, C_IN, C_OUT = 8, 12, 2, 5
-N_PARAMS, N_BN, MAX_PEDS = 7563, 30, 256
+N_PARAMS, N_BN, MAX_PEDS, MAX_RANKS = 7563, 30, 256, 8
 XTILE_COLS, XTILE_MAX_SCENES, XTILE_MAX_PAIRS = 128, 32, 64
 ST_PARAMS, TXP_GRAD_STRIDE, SAVE_FLOATS_PER_PED = 142, 7424, 600
 GRAPH_NORM_LAP, GRAPH_FP64, GRAPH_V_ONLY = 1, 2, 4
@@ -56,6 +56,18 @@ _SIGS.update({
     "sstg_peer_exchange_apply": (C.c_int, [C.POINTER(C.c_void_p), _i32, _i32, C.c_uint32, _i32, _p, _p, _p, _i32, _i32,
                                            _p, _i32, _p, _p, _f32, _f32, _f64, _p, _p, _p, _p, C.c_uint64, _p]),
 })
+
+
+
+class PeerRank(C.Structure):
+    """sstg_peer_rank (include/sstg.h): one rank's arguments of sstg_peer_exchange_apply_local."""
+    _fields_ = [("rank", _i32), ("scene_lo", _i32), ("s_local", _i32), ("reserved", _i32),
+                ("grad_local", _p), ("loss_local", _p), ("stats_local", _p), ("seg_off_all", _p),
+                ("params", _p), ("bn", _p), ("grad_out", _p), ("loss_out", _p), ("stats_out", _p), ("status", _p)]
+
+
+_SIGS["sstg_peer_exchange_apply_local"] = (C.c_int, [C.POINTER(C.c_void_p), _i32, C.POINTER(PeerRank), _i32, C.c_uint32,
+                                                     _i32, _i32, _f32, _f32, _f64, C.c_uint64, _p])
 
 _lock = threading.Lock()
 _lib = None

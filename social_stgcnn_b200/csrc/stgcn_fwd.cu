@@ -171,17 +171,18 @@ stgcn_fwd_kernel(const float* __restrict__ V, const float* __restrict__ A, const
   uint32_t consumed = 0;  // chunks consumed by this warp so far (stage = consumed % STAGES)
   // V[t] of the first scene
   float vx[NJ], vy[NJ];
-#ifdef SSTG_STGCN_PREFETCH_OFFSETS
-  // A/B variant (not the default, not yet measured): the next scene's offsets travel with its V prefetch, so the scene
-  // top does not wait for a dependent global load -> use chain (6 % of the stall samples sit on its first consumer,
-  // profiles/r1t_ncu_full_summary.csv / scripts/ncu_stalls.py)
+#ifndef SSTG_STGCN_NO_PREFETCH_OFFSETS
+  // The next scene's offsets travel with its V prefetch, so the scene top does not wait for a dependent global
+  // load -> use chain (6 % of the stall samples sat on its first consumer, profiles/r1t_ncu_full_summary.csv):
+  // 3.44 -> 3.33 ms per 131,072 scenes of 64, bit-identical (profiles/r2a_ab_stgcn_po.txt).
+  // -DSSTG_STGCN_NO_PREFETCH_OFFSETS restores the in-loop loads for A/B runs.
   int nx_n0 = 0, nx_N = 1;
   long long nx_ao = 0;
 #endif
   auto load_v = [&](int s) {
     if (s < S) {
       const int n0 = seg_off[s], N = seg_off[s + 1] - n0;
-#ifdef SSTG_STGCN_PREFETCH_OFFSETS
+#ifndef SSTG_STGCN_NO_PREFETCH_OFFSETS
       nx_n0 = n0;
       nx_N = N;
       nx_ao = a_off[s];
@@ -200,7 +201,7 @@ stgcn_fwd_kernel(const float* __restrict__ V, const float* __restrict__ A, const
 
   int it = 0;
   for (int s = blockIdx.x; s < S; s += gridDim.x, ++it) {
-#ifdef SSTG_STGCN_PREFETCH_OFFSETS
+#ifndef SSTG_STGCN_NO_PREFETCH_OFFSETS
     const int n0 = nx_n0;
     const int N = nx_N;
     const float* sl = A + nx_ao + static_cast<size_t>(t) * N * N;

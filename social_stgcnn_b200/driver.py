@@ -79,7 +79,7 @@ def epoch_rows(seg_off, n_peds, order):
 
 
 def train_epoch(dataset, engine: E.TrainEngine, batch_size: int = 128, lr: float = 0.01,
-                clip_grad: Optional[float] = None, order=None, trainer=None):
+                clip_grad: Optional[float] = None, order=None, trainer=None, check_every: int = 32):
     """train() of the reference (train.py:28-79) over one epoch.
 
     `order` is the scene order of the epoch (the DataLoader's shuffle; default: dataset order).
@@ -87,7 +87,10 @@ def train_epoch(dataset, engine: E.TrainEngine, batch_size: int = 128, lr: float
     SGD step, with the reference's accumulation rule (the last scene of a group is forwarded but
     not scored, divisor batch_size; train.py:58-66).  Returns loss_batch / batch_count exactly as
     the reference does (sum of the group losses / number of scenes, train.py:76-79).
-    `trainer` (parallel.DistributedTrainer) spreads every group over the ranks."""
+    `trainer` (parallel.DistributedTrainer) spreads every group over the ranks.  Every rank must then
+    pass the SAME `order` (fit() broadcasts rank 0's shuffle): this is verified with one small collective
+    per epoch, which also lines the ranks up before the first peer-memory exchange, and the exchange status
+    is checked on all ranks together every `check_every` groups and at the end of the epoch."""
     dev = engine.device
     pk = _packed(dataset, dev)
     S = len(dataset)
@@ -96,6 +99,16 @@ def train_epoch(dataset, engine: E.TrainEngine, batch_size: int = 128, lr: float
     seg = np.asarray(dataset.plan_obs.seg_off, np.int64)
     if S == 0:
         return 0.0
+    sharded = trainer is not None and getattr(trainer, "world", 1) > 1
+    if sharded:
+        # Ranks that disagreed on the epoch order would shard DIFFERENT scenes of every group (some counted twice,
+        # some never, BatchNorm rows overlapping) without any error.  The collective doubles as the barrier that
+        # bounds host-side skew (dataset parsing, a checkpoint write, lazy module loading) before the first
+        # exchange kernel starts its bounded wait.
+        from . import parallel as Pl
+        Pl.assert_same_across_ranks((np.asarray(order, np.int64), n_all[np.asarray(order, np.int64)],
+                                     np.asarray([batch_size], np.int64)), trainer.group, dev,
+                                    what="train_epoch: scene order / pedestrian counts / batch_size")
     # ---- the epoch is prepared in one pass (the per-group device time is ~0.13 ms, so anything done per
     # group on the host decides the epoch time): ONE gather of the pedestrian rows in epoch order -- every
     # group is then a contiguous slice -- and ONE upload of all the groups' offset tables
@@ -115,27 +128,57 @@ def train_epoch(dataset, engine: E.TrainEngine, batch_size: int = 128, lr: float
         obs, pred = obs_e[p0:p1], pred_e[p0:p1]
         if trainer is not None:
             losses[gi].copy_(trainer.step(n_all[groups[gi]], obs, pred, batch_size, lr, clip_grad, presliced=False))
+            if sharded and check_every > 0 and (gi + 1) % check_every == 0 and gi + 1 < len(groups):
+                trainer.check()         # a rank that never delivered: every rank raises, together
         else:
             losses[gi].copy_(engine.step(plans[gi], obs, pred, batch_size, lr, clip_grad))
-    if trainer is not None and getattr(trainer, "peer", None) is not None:
-        trainer.peer.check()            # a rank that never delivered: raise instead of training on
+    if trainer is not None:
+        trainer.check()
     return float(losses.double().sum()) / S
+
+
+def vald_accumulate(scene_loss, batch_size: int) -> float:
+    """The bookkeeping of vald() (train.py:81-122) on the per-scene eval losses, in loader order: groups of
+    `batch_size` scenes, the last scene of a group unscored, divisor batch_size, result = sum of the group
+    losses / number of scenes.  A trailing group of exactly ONE scene (len % batch_size == 1) scores nothing
+    itself: there the reference divides the PREVIOUS group's already divided loss by batch_size once more
+    and adds that (train.py:115-119: `loss` still holds the last group's value); with no previous group it
+    raises UnboundLocalError -- mirrored here."""
+    loss = np.asarray(scene_loss, np.float64)
+    S = int(loss.size)
+    if S == 0:
+        return 0.0
+    tot, prev = 0.0, None
+    for g0 in range(0, S, batch_size):
+        g = loss[g0:g0 + batch_size]
+        if g.size == 1:
+            if prev is None:
+                raise UnboundLocalError("cannot access local variable 'loss' where it is not associated with a "
+                                        "value (vald() of train.py with a single scene)")
+            cur = prev / batch_size
+        else:
+            cur = float(g[:-1].sum()) / batch_size
+        tot += cur
+        prev = cur
+    return tot / S
 
 
 def validate_epoch(dataset, engine: E.InferenceEngine, batch_size: int = 128):
     """vald() of the reference (train.py:81-122): eval-mode forward, same accumulation rule,
-    no parameter update.  Returns loss_batch / batch_count."""
+    no parameter update.  Returns loss_batch / batch_count.  The dataset's packed V_obs / A_obs / V_tr
+    blocks (built once, bit-identical to the reference's graphs) are fed straight to the forward
+    kernels: no graph build and no sampling per epoch."""
     dev = engine.device
     pk = _packed(dataset, dev)
     plan = dataset.plan_obs
-    r = engine.infer(plan, pk["obs_rel"], pk["pred_rel"], pk["last_obs"], K=1, graph_fp64=True)
-    loss = E.nll_forward(plan.on(dev), r["V_pred"], r["V_tr"]).double().cpu().numpy()
-    S = plan.S
-    tot = 0.0
-    for g0 in range(0, S, batch_size):
-        g = loss[g0:g0 + batch_size]
-        tot += float(g[:-1].sum()) / batch_size
-    return tot / S
+    if plan.S == 0:
+        return 0.0
+    dp = plan.on(dev)
+    ws = engine.workspace(plan)
+    E.stgcn_forward(dp, pk["V_obs"], pk["A_obs"], engine.params, engine.bn, H=ws["H"])
+    E.txpcnn_forward(dp, ws["H"], engine.params, out=ws["V_pred"])
+    loss = E.nll_forward(dp, ws["V_pred"], pk["V_tr"]).double().cpu().numpy()
+    return vald_accumulate(loss, batch_size)
 
 
 def fit(train_set, val_set, engine: E.TrainEngine, *, num_epochs: int = 250, batch_size: int = 128, lr: float = 0.01,
@@ -145,21 +188,37 @@ def fit(train_set, val_set, engine: E.TrainEngine, *, num_epochs: int = 250, bat
     train_epoch and a validate_epoch, StepLR(step_size=lr_sh_rate, gamma=0.2) when `use_lrschd`,
     and -- in `checkpoint_dir` -- exactly the artefacts the reference writes: `args.pkl`,
     `val_best.pth` (the 40-key state_dict, on every new best validation loss), `metrics.pkl`,
-    `constant_metrics.pkl`.  Returns (metrics, constant_metrics)."""
+    `constant_metrics.pkl`.  Returns (metrics, constant_metrics).
+    With a `trainer` (parallel.DistributedTrainer) every epoch's shuffle is drawn on rank 0 and broadcast,
+    and rank 0 alone writes the artefacts (each file is written to a temporary name and renamed)."""
     import os
     import pickle
+    from . import parallel as Pl
+    world, rank = (trainer.world, trainer.rank) if trainer is not None else (1, 0)
+    group = trainer.group if trainer is not None else None
     rng = np.random.default_rng(seed)
     val_eng = E.InferenceEngine(engine.params.cpu().numpy(), engine.bn.cpu().numpy(), engine.device)
-    if checkpoint_dir:
+    writer = bool(checkpoint_dir) and rank == 0       # replicas are identical: rank 0 alone writes the artefacts
+
+    def dump(name, obj, save=pickle.dump):
+        # whole-file replace: a reader (or a crash) never sees a half-written checkpoint
+        path = os.path.join(checkpoint_dir, name)
+        tmp = f"{path}.tmp.{os.getpid()}"
+        with open(tmp, "wb") as fp:
+            save(obj, fp)
+        os.replace(tmp, path)
+
+    if writer:
         os.makedirs(checkpoint_dir, exist_ok=True)
         if args is not None:
-            with open(os.path.join(checkpoint_dir, "args.pkl"), "wb") as fp:
-                pickle.dump(args, fp)
+            dump("args.pkl", args)
     metrics = {"train_loss": [], "val_loss": []}
     constant_metrics = {"min_val_epoch": -1, "min_val_loss": 9999999999999999}
     cur_lr = lr
     for epoch in range(num_epochs):
         order = rng.permutation(len(train_set))                 # DataLoader(shuffle=True), train.py:173-177
+        if world > 1:                                           # every rank trains on RANK 0's shuffle
+            order = Pl.broadcast_order(order, group, engine.device)
         metrics["train_loss"].append(train_epoch(train_set, engine, batch_size, cur_lr, clip_grad, order, trainer))
         val_eng.load_weights(engine.params, engine.bn)
         metrics["val_loss"].append(validate_epoch(val_set, val_eng, batch_size))
@@ -168,14 +227,12 @@ def fit(train_set, val_set, engine: E.TrainEngine, *, num_epochs: int = 250, bat
         if metrics["val_loss"][-1] < constant_metrics["min_val_loss"]:
             constant_metrics["min_val_loss"] = metrics["val_loss"][-1]
             constant_metrics["min_val_epoch"] = epoch
-            if checkpoint_dir:
-                torch.save(engine.state_dict(), os.path.join(checkpoint_dir, "val_best.pth"))
-        if log:
+            if writer:
+                dump("val_best.pth", engine.state_dict(), torch.save)
+        if log and rank == 0:
             log(f"epoch {epoch}: train_loss {metrics['train_loss'][-1]:.6f} val_loss {metrics['val_loss'][-1]:.6f} "
                 f"lr {cur_lr:g} {constant_metrics}")
-        if checkpoint_dir:
-            with open(os.path.join(checkpoint_dir, "metrics.pkl"), "wb") as fp:
-                pickle.dump(metrics, fp)
-            with open(os.path.join(checkpoint_dir, "constant_metrics.pkl"), "wb") as fp:
-                pickle.dump(constant_metrics, fp)
+        if writer:
+            dump("metrics.pkl", metrics)
+            dump("constant_metrics.pkl", constant_metrics)
     return metrics, constant_metrics

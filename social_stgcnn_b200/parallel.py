@@ -104,6 +104,50 @@ def gather_scene_stats(stats_local: torch.Tensor, counts: Sequence[int], group=N
     return torch.cat([o[:c] for o, c in zip(out, counts)], dim=0)
 
 
+def _coll_device(group=None, device=None):
+    """Where a small host-logic collective has to live: the GPU for NCCL, the CPU for gloo."""
+    backend = dist.get_backend(group) if (dist.is_available() and dist.is_initialized()) else "gloo"
+    if "nccl" in str(backend) and device is not None and torch.device(device).type == "cuda":
+        return torch.device(device)
+    return torch.device("cpu")
+
+
+def broadcast_order(order, group=None, device=None, src: int = 0) -> np.ndarray:
+    """Rank `src`'s epoch order (the DataLoader shuffle of train.py:173-177) on every rank.  The sharded
+    optimiser group is only meaningful when all ranks cut the SAME scene sequence into groups."""
+    order = np.ascontiguousarray(np.asarray(order, np.int64).reshape(-1))
+    world, _ = _world(group)
+    if world == 1:
+        return order
+    t = torch.from_numpy(order.copy()).to(_coll_device(group, device))
+    dist.broadcast(t, src=dist.get_global_rank(group, src) if group is not None else src, group=group)
+    return t.cpu().numpy()
+
+
+def assert_same_across_ranks(arrays, group=None, device=None, what: str = "arguments") -> None:
+    """Raise ValueError on EVERY rank when the ranks do not hold byte-identical `arrays` (one 4-element
+    all-reduce of two 63-bit digests and their negations: max(x) == -max(-x) iff all ranks agree).  It is
+    also a barrier."""
+    world, _ = _world(group)
+    if world == 1:
+        return
+    import hashlib
+    h = hashlib.blake2b(digest_size=16)
+    for a in arrays:
+        a = np.ascontiguousarray(a)
+        h.update(str((a.dtype.str, a.shape)).encode())
+        h.update(a.tobytes())
+    d = h.digest()
+    x0 = int.from_bytes(d[:8], "little") >> 1
+    x1 = int.from_bytes(d[8:], "little") >> 1
+    t = torch.tensor([x0, -x0, x1, -x1], dtype=torch.int64, device=_coll_device(group, device))
+    dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+    t = t.cpu()
+    if int(t[0]) != -int(t[1]) or int(t[2]) != -int(t[3]):
+        raise ValueError(f"{what} differ between ranks: every rank of a sharded group must pass the same values "
+                         "(draw the shuffle once and broadcast it -- parallel.broadcast_order)")
+
+
 def bind_process_to_gpu_numa(device_index: int) -> Optional[int]:
     """Pin this process to the CPUs of the NUMA node its GPU hangs off (read from sysfs), BEFORE the
     pinned host buffers are allocated, so that first-touch places them next to the GPU's PCIe root
@@ -158,13 +202,20 @@ class PeerExchange:
 
     All ranks must sit on one node (NVLink/NVSwitch peer access) and call `exchange` in lockstep."""
 
-    def __init__(self, device, max_scenes: int = 256, group=None, timeout_s: float = 5.0, *, _shared=None):
+    def __init__(self, device, max_scenes: int = 256, group=None, timeout_s: float = 30.0, *, _shared=None):
+        import atexit
         import ctypes as C
+        import weakref
+        # the IPC mappings and the cudaMalloc'd mailbox are not torch memory: release them when the object goes
+        # away or at interpreter exit (close() is idempotent)
+        self._own, self._opened = None, []
+        ref = weakref.ref(self)
+        atexit.register(lambda: ref() is not None and ref()._close_quietly())
         lib = L.load()
         self.device = torch.device(device)
         self.group, self.max_scenes, self.epoch = group, int(max_scenes), 0
         self.timeout_ns = int(timeout_s * 1e9)
-        self._own, self._opened = None, []
+        self._emulated = _shared is not None
         if _shared is not None:                      # several ranks emulated inside one process (tests)
             self.world, self.rank, ptrs = _shared
         else:
@@ -220,7 +271,7 @@ class PeerExchange:
         self.stats = torch.zeros(max(self.max_scenes, 1), L.N_BN, dtype=torch.float32, device=self.device)
 
     @classmethod
-    def local_group(cls, world: int, max_scenes: int, device, timeout_s: float = 5.0):
+    def local_group(cls, world: int, max_scenes: int, device, timeout_s: float = 30.0):
         """`world` exchanges that live in THIS process on one GPU (each rank's kernel goes on its own
         stream): the protocol, runnable on a single-GPU box."""
         import ctypes as C
@@ -237,6 +288,9 @@ class PeerExchange:
             ptrs.append(q.value)
         out = [cls(device, max_scenes, None, timeout_s, _shared=(world, r, ptrs)) for r in range(world)]
         out[0]._owned_all = ptrs
+        local = _LocalRanks(world, device)
+        for pe in out:
+            pe._local = local
         return out
 
     def exchange(self, engine, grad_local, loss_local, stats_local, scene_lo: int, s_local: int, seg_off_all,
@@ -247,6 +301,17 @@ class PeerExchange:
             raise ValueError(f"group of {s_all} scenes exceeds the mailbox capacity {self.max_scenes}")
         self.epoch += 1
         ptr = lambda t: t.data_ptr() if isinstance(t, torch.Tensor) else (t or None)
+        if self._emulated:
+            # ranks that share this process and device: queue the arguments; the group goes out as ONE
+            # cooperative launch when its last rank has called (or at flush() / check())
+            one = L.PeerRank(self.rank, int(scene_lo), int(s_local), 0, ptr(grad_local), ptr(loss_local),
+                             ptr(stats_local), ptr(seg_off_all), engine.params.data_ptr(), engine.bn.data_ptr(),
+                             engine.grad.data_ptr(), self.loss.data_ptr(), self.stats.data_ptr(),
+                             self.status.data_ptr())
+            self._local.submit(self, one, (self.epoch, int(s_all), float(lr), float(clip_norm or 0.0),
+                                           float(bn_momentum)),
+                               keep=(grad_local, loss_local, stats_local, seg_off_all, engine))
+            return self.loss[0]
         if stream is None:
             stream = torch.cuda.current_stream(self.device).cuda_stream
         with torch.cuda.device(self.device):
@@ -258,12 +323,42 @@ class PeerExchange:
                 "sstg_peer_exchange_apply")
         return self.loss[0]
 
-    def check(self):
-        """Synchronise and raise if any exchange since the last check timed out."""
-        st = int(self.status.item())
+    def check(self, shared: bool = True):
+        """Synchronise and raise if any exchange since the last check failed.  The status word is sticky: after a
+        time-out this rank's exchange kernels refuse to run (no push, no update), so its peers time out too and
+        NO replica trains on.  With `shared` (real multi-process groups) the status is max-reduced over the
+        ranks first, so that every rank raises at the same check instead of the late one alone."""
+        if self._emulated:
+            self._local.flush()
+            if self._local.done is not None:
+                self._local.done.synchronize()        # the group ran on its own stream
+        st = self.status
+        if shared and not self._emulated and self.world > 1 and dist.is_available() and dist.is_initialized():
+            st = st.clone()
+            dist.all_reduce(st, op=dist.ReduceOp.MAX, group=self.group)
+        st = int(st.item())
         if st:
-            raise RuntimeError(f"peer exchange: rank {st - 1} did not deliver within {self.timeout_ns / 1e9:.1f} s "
-                               f"(this is rank {self.rank}); weights were left untouched")
+            own = int(self.status.item())
+            who = f"rank {own - 1} did not deliver to rank {self.rank}" if own else \
+                f"an exchange failed on another rank (first late source there: rank {st - 1})"
+            raise RuntimeError(f"peer exchange: {who} within {self.timeout_ns / 1e9:.1f} s; the replicas may have "
+                               "diverged -- restart from the last checkpoint")
+
+    def wait_previous(self):
+        """Order the caller's current stream after the last exchange this rank took part in.  A no-op for real
+        ranks (their exchange runs on the caller's stream); ranks emulated in one process are launched together
+        on the group's stream."""
+        if self._emulated:
+            self._local.wait(torch.cuda.current_stream(self.device))
+
+    def _close_quietly(self):
+        try:
+            self.close()
+        except Exception:                                           # noqa: BLE001 -- interpreter / context teardown
+            pass
+
+    def __del__(self):
+        self._close_quietly()
 
     def close(self):
         lib = L.load()
@@ -277,6 +372,51 @@ class PeerExchange:
             for q in getattr(self, "_owned_all", []) or ([self._own] if self._own else []):
                 lib.sstg_peer_free(q)
             self._own, self._owned_all = None, []
+
+
+class _LocalRanks:
+    """Several ranks of one exchange group inside ONE process on ONE device (PeerExchange.local_group): their
+    exchange kernels wait on one another, so they are issued as ONE cooperative launch
+    (sstg_peer_exchange_apply_local) -- separate launches are not guaranteed to be co-resident."""
+
+    def __init__(self, world: int, device):
+        self.world, self.device = int(world), torch.device(device)
+        self.stream = torch.cuda.Stream(self.device)
+        self.pending, self.common, self.done = {}, None, None
+
+    def submit(self, pe, one, common, keep):
+        if pe.rank in self.pending or (self.common is not None and common != self.common):
+            self.flush()                              # a rank came round again before the others: issue what there is
+        self.common = common
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.device))
+        self.pending[pe.rank] = (pe, one, ev, keep)
+        if len(self.pending) == self.world:
+            self.flush()
+
+    def flush(self):
+        if not self.pending:
+            return
+        import ctypes as C
+        items = [self.pending[r] for r in sorted(self.pending)]
+        pe0 = items[0][0]
+        arr = (L.PeerRank * len(items))(*[it[1] for it in items])
+        epoch, s_all, lr, clip, mom = self.common
+        for it in items:
+            self.stream.wait_event(it[2])             # every queued rank's shard results are ready
+        with torch.cuda.device(self.device):
+            L.check(L.load().sstg_peer_exchange_apply_local(pe0._boxes, self.world, arr, len(items), epoch,
+                                                            pe0.max_scenes, s_all, lr, clip, mom, pe0.timeout_ns,
+                                                            self.stream.cuda_stream),
+                    "sstg_peer_exchange_apply_local")
+        self.done = torch.cuda.Event()
+        self.done.record(self.stream)
+        self._keep = [it[3] for it in items]          # until the next flush: the launch reads these buffers
+        self.pending, self.common = {}, None
+
+    def wait(self, stream):
+        if self.done is not None:
+            stream.wait_event(self.done)
 
 
 class _ShardedGroup:
@@ -338,11 +478,12 @@ class DistributedTrainer:
     exchange = "peer": libsstg.so's one-kernel exchange over NVLink peer memory (PeerExchange), fused
                        with the SGD step -- two library calls per group, no torch op in between;
                "nccl": one torch.distributed all-reduce of [gradient | loss | statistics rows];
-               "auto": "peer" when every rank is on CUDA on one node and world <= 8 (env
-                       SSTG_EXCHANGE=nccl|peer overrides), else "nccl"."""
+               "auto": "peer" when every rank is on CUDA on one node and world <= SSTG_MAX_RANKS (8), else
+                       "nccl"; the environment variable SSTG_EXCHANGE=nccl|peer decides for "auto" only -- an
+                       explicit "peer" / "nccl" argument is never overridden."""
 
     def __init__(self, engine, group=None, exchange: str = "auto", max_scenes: int = 256, *,
-                 peer_timeout_s: float = 5.0, _emulate=None):
+                 peer_timeout_s: float = 30.0, _emulate=None):
         import os
         self.engine, self.group = engine, group
         self._flat, self._groups = {}, {}
@@ -350,13 +491,22 @@ class DistributedTrainer:
         if _emulate is not None:       # a PeerExchange.local_group member: several ranks inside one process (tests)
             self.peer, self.exchange = _emulate, "peer"
             self._wr = (_emulate.world, _emulate.rank)
+            self.world, self.rank = self._wr
             return
-        world, _ = _world(group)
-        mode = os.environ.get("SSTG_EXCHANGE", exchange)
-        if mode not in ("auto", "peer", "nccl"):
+        world, rank = _world(group)
+        self.world, self.rank = world, rank
+        if exchange not in ("auto", "peer", "nccl"):
             raise ValueError("exchange must be auto, peer or nccl")
+        mode = exchange
+        if exchange == "auto" and os.environ.get("SSTG_EXCHANGE"):
+            mode = os.environ["SSTG_EXCHANGE"]
+            if mode not in ("auto", "peer", "nccl"):
+                raise ValueError("SSTG_EXCHANGE must be auto, peer or nccl")
+        if mode == "peer" and world > L.MAX_RANKS:
+            raise ValueError(f"exchange='peer' handles at most SSTG_MAX_RANKS = {L.MAX_RANKS} ranks on one node "
+                             f"(world size is {world}); use exchange='nccl'")
         self.peer = None
-        if world > 1 and world <= 8 and (mode == "peer" or (mode == "auto" and engine.device.type == "cuda")):
+        if 1 < world <= L.MAX_RANKS and (mode == "peer" or (mode == "auto" and engine.device.type == "cuda")):
             try:
                 self.peer = PeerExchange(engine.device, max_scenes, group, timeout_s=peer_timeout_s)
                 ok = 1
@@ -372,6 +522,12 @@ class DistributedTrainer:
                 self.peer.close()
                 self.peer = None
         self.exchange = "peer" if self.peer is not None else ("nccl" if world > 1 else "none")
+
+    def check(self):
+        """Raise on every rank if a peer-memory exchange since the last check failed on any rank (no-op for
+        the NCCL exchange, whose collectives fail by themselves)."""
+        if self.peer is not None:
+            self.peer.check(shared=self._wr is None)
 
     def prepare(self, n_peds_list, batch_size: int):
         """Host preparation of many groups at once (driver.train_epoch calls it with the epoch's groups): their
@@ -417,6 +573,7 @@ class DistributedTrainer:
         if self.peer is not None:
             # library call 1: this shard's graph build + forward + backward (no update);
             # library call 2: exchange over peer memory + SGD + BN recurrence in global scene order
+            self.peer.wait_previous()
             grad_l, loss_l, stats_l = eng.shard_forward_backward(g.plan, o, p, g.w_dev, graph_fp64=graph_fp64)
             out = self.peer.exchange(eng, grad_l, loss_l, stats_l, lo, hi - lo, g.seg_all_dev, g.S_all, lr,
                                      clip_grad or 0.0)

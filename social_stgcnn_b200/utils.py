@@ -98,31 +98,39 @@ def _scenes_of_file(data, seq_len, skip, min_ped, pred_len, threshold):
     """Sliding windows of one file (utils.py:121-170), vectorised: a pedestrian belongs to a
     window iff it is present at the window's first and last frame (pad_front == 0 and
     pad_end == seq_len, utils.py:146-149).  Yields (abs (n,2,L), rel (n,2,L), non_linear (n,),
-    peds_seen) per kept window, pedestrians in ascending id order like np.unique."""
+    peds_seen) per kept window, pedestrians in ascending id order like np.unique.
+    Memory is O(rows) like the reference's: the rows are sorted by frame once, a window is the
+    contiguous row range of its seq_len frames (no dense pedestrian x frame table, which long
+    recordings with many track ids would blow up)."""
     frames, fi = np.unique(data[:, 0], return_inverse=True)
-    _, pi = np.unique(data[:, 1], return_inverse=True)
-    F, Pn = frames.size, int(pi.max()) + 1
-    count = np.zeros((Pn, F), np.int32)
-    np.add.at(count, (pi, fi), 1)
-    rowid = np.full((Pn, F), -1, np.int64)
-    rowid[pi, fi] = np.arange(data.shape[0])
-    xy = np.around(data[:, 2:4], decimals=4)                      # utils.py:145
+    F = frames.size
+    by_frame = np.argsort(fi, kind="stable")                      # frame order, file order inside a frame
+    fi_s = fi[by_frame]
+    ped_s = data[by_frame, 1]
+    xy_s = np.around(data[by_frame, 2:4], decimals=4)             # utils.py:145
+    frame_start = np.searchsorted(fi_s, np.arange(F + 1))         # rows of frame f: [frame_start[f], frame_start[f+1])
     num_sequences = int(math.ceil((F - seq_len + 1) / skip))
     for idx in range(0, num_sequences * skip + 1, skip):          # "+ 1" as in utils.py:129
-        win = count[:, idx:idx + seq_len]
-        seen = int((win.sum(1) > 0).sum())
-        if win.shape[1] < seq_len:                                # trailing short window: nobody can span it
+        lo, hi = frame_start[min(idx, F)], frame_start[min(idx + seq_len, F)]
+        ids, inv, cnt = np.unique(ped_s[lo:hi], return_inverse=True, return_counts=True)
+        seen = int(ids.size)
+        if idx + seq_len > F:                                     # trailing short window: nobody can span it
             yield None, None, None, seen
             continue
-        ok = (win[:, 0] > 0) & (win[:, -1] > 0)
-        if np.any(ok & (win.sum(1) != seq_len)):
+        rel_f = fi_s[lo:hi] - idx
+        first = np.bincount(inv[rel_f == 0], minlength=seen) > 0
+        last = np.bincount(inv[rel_f == seq_len - 1], minlength=seen) > 0
+        ok = first & last
+        if np.any(ok & (cnt != seq_len)):
             raise ValueError("could not broadcast input array: a pedestrian spans the window but misses "
                              "frames inside it")               # what utils.py:158 would raise
-        sel = np.nonzero(ok)[0]
-        if sel.size <= min_ped:                                   # utils.py:165
+        n = int(ok.sum())
+        if n <= min_ped:                                          # utils.py:165
             yield None, None, None, seen
             continue
-        seq = xy[rowid[sel, idx:idx + seq_len]].transpose(0, 2, 1)   # (n, 2, L)
+        rows = np.nonzero(ok[inv])[0]                             # window rows of the kept pedestrians ...
+        rows = rows[np.argsort(inv[rows], kind="stable")]         # ... by pedestrian id, frame order inside
+        seq = xy_s[lo + rows].reshape(n, seq_len, 2).transpose(0, 2, 1)   # (n, 2, L)
         rel = np.zeros_like(seq)
         rel[:, :, 1:] = seq[:, :, 1:] - seq[:, :, :-1]              # utils.py:153-155
         nl = _poly_fit_batch(seq, pred_len, threshold)
@@ -199,6 +207,11 @@ class TrajectoryDataset(Dataset):
             data_dir, obs_len, pred_len, skip, threshold, min_ped, delim)
 
         self.num_seq = len(seqs)
+        from ._lib import MAX_PEDS
+        if counts and max(counts) > MAX_PEDS:
+            raise ValueError(f"{data_dir}: a window holds {max(counts)} pedestrians, but the kernels of libsstg.so "
+                             f"accept at most SSTG_MAX_PEDS = {MAX_PEDS} per scene (include/sstg.h; shared-memory "
+                             "bound of the st_gcn / graph kernels)")
         seq_all = np.concatenate(seqs, axis=0)
         rel_all = np.concatenate(rels, axis=0)
         f32 = lambda a: torch.from_numpy(np.ascontiguousarray(a)).type(torch.float)

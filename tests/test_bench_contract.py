@@ -24,6 +24,12 @@ def test_reference_arm_prints_one_contract_line():
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
     assert "workload" in d["config"] and d["config"]["peds_per_scene"] == 64
+    # the reference arm reports exactly the configuration our arm reports (both call bench_config)
+    sys.path.insert(0, ROOT)
+    import bench
+    assert d["config"] == bench.bench_config(131072, 1)
+    src = open(os.path.join(ROOT, "bench.py")).read()
+    assert src.count('"config": bench_config(') == 2
 
 
 def test_our_arm_refuses_to_run_without_cuda():

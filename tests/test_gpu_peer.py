@@ -1,9 +1,10 @@
 """GPU tests of the peer-memory gradient exchange (sstg_peer_exchange_apply, include/sstg.h): the
 scene-sharded optimiser group must reproduce the single-GPU group (TrainEngine.step).
 
-On a one-GPU box the ranks are emulated inside one process (PeerExchange.local_group: one mailbox and
-one stream per rank, the same kernel and protocol); with >= 2 GPUs a second test runs real processes
-over CUDA IPC + NVLink and compares with the NCCL exchange.
+On a one-GPU box the ranks are emulated inside one process (PeerExchange.local_group: one mailbox per rank,
+the same kernel and protocol; because the ranks' CTAs wait on one another they are issued as ONE cooperative
+launch, sstg_peer_exchange_apply_local -- never as separate launches that may not be co-resident); with
+>= 2 GPUs a second test runs real processes over CUDA IPC + NVLink and compares with the NCCL exchange.
 
 Tolerances: the sharded gradient is the same per-scene terms summed in a different order (per-rank
 partial sums, then rank order), so weights after a step agree to fp32 rounding of the gradient
@@ -102,6 +103,19 @@ def test_missing_peer_times_out_and_leaves_weights_alone(golden, dev):
             peers[0].check()
         assert np.array_equal(eng.params.cpu().numpy(), params.astype(np.float32).reshape(-1))
         assert np.array_equal(eng.bn.cpu().numpy(), bn.astype(np.float32).reshape(-1))
+        # the status word is sticky: the failed rank takes no part in later exchanges (returns at once, pushes
+        # nothing, applies nothing) until the caller clears it
+        flags_before = peers[0].epoch
+        t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
+        t0.record()
+        tr.step(n, torch.from_numpy(obs).to(dev), torch.from_numpy(pred).to(dev), 6, 1e-3)
+        with pytest.raises(RuntimeError, match="rank 1 did not deliver"):
+            tr.check()
+        t1.record()
+        torch.cuda.synchronize()
+        assert t0.elapsed_time(t1) < 45.0                                  # no second 50 ms wait
+        assert peers[0].epoch == flags_before + 1
+        assert np.array_equal(eng.params.cpu().numpy(), params.astype(np.float32).reshape(-1))
     finally:
         peers[0].close()
 

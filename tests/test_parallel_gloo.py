@@ -136,6 +136,18 @@ def _worker(rank, world, port, ret):
         assert updates["stats"].shape == (8, 30)
         assert torch.equal(updates["stats"][:, 0], torch.arange(8, dtype=torch.float32))   # global order
         assert eng.num_batches_tracked == 8
+        assert tr.world == world and tr.rank == rank and tr.exchange == "nccl"
+        tr.check()                                                         # no peer exchange: nothing to report
+        # ---- the epoch shuffle: rank 0's permutation reaches every rank; a rank with its own order is caught
+        mine = np.random.default_rng(100 + rank).permutation(37)           # what an unseeded fit() would draw
+        order = Pl.broadcast_order(mine)
+        assert np.array_equal(order, np.random.default_rng(100).permutation(37))
+        Pl.assert_same_across_ranks((order, np.arange(5)))                 # agree: passes (and is a barrier)
+        try:
+            Pl.assert_same_across_ranks((mine,), what="epoch order")       # disagree: EVERY rank raises
+            raise AssertionError("mismatch not detected")
+        except ValueError as e:
+            assert "epoch order differ between ranks" in str(e)
         # both replicas end bit-identical
         blob = torch.cat([eng.params, eng.bn])
         both = [torch.empty_like(blob) for _ in range(world)]
