@@ -16,11 +16,17 @@
 //     Because a ragged packed batch cannot guarantee 16-byte aligned rows, each copy is
 //     the 16-byte-aligned superset of the rows it needs and the consumer indexes into it
 //     with the residual offset.
-//   * lanes own output columns w; each A element is read from shared memory exactly once
-//     and feeds 5 FMAs (one per channel) against a broadcast g[., t, v].
+//   * lanes own output columns w = lane + 32 j.  The aggregation is issue-limited, not FMA-limited
+//     (profiles/r2d: 19.5 instructions per 64-element row, 62 % of the issue slots, 2,460 instructions per
+//     warp and scene of which only 1,090 were the row loop), so every FMA is a packed FFMA2 over a PAIR OF
+//     ROWS: accumulator (sum over even rows, sum over odd rows) += (A[v][w], A[v+1][w]) * (g[c][v], g[c][v+1]).
+//     The pair of A values is two LDS.32 into adjacent registers (any N, no alignment requirement), the g
+//     pairs of FOUR rows of a channel are one broadcast LDS.128 out of a [row quad][channel][4] tile, and
+//     a chunk always holds a multiple of four rows: 8.25 + ~2 instructions per 64-element row.
 //   * BN (eval) is folded into scale/offset pairs once per CTA; the temporal conv needs the
 //     neighbouring timesteps, i.e. other warps' results, through a double-buffered
-//     shared tile and ONE __syncthreads per scene.
+//     shared tile and ONE __syncthreads per scene; it runs as FFMA2 over the lane's column pair
+//     (lane, lane + 32) against (w, w) pairs kept duplicated in shared memory.
 #include <cstdlib>
 
 #include "sstg_common.cuh"
@@ -32,13 +38,23 @@ namespace {
 constexpr int S_WARPS = T_OBS;  // one warp per observed timestep
 constexpr int S_THREADS = S_WARPS * 32;
 constexpr int S_MAX_STAGES = 4;
-constexpr int S_PAD = 8;  // floats of slack per stage for the aligned-superset copies
+constexpr int S_PAD = 8;       // floats of slack per stage for the aligned-superset copies
+constexpr int G_QUAD = 4 * C;  // floats per row quad of the g tile: [channel][4 rows]
 
-struct FoldedParams {
+// packed FP32 (sm_100 FFMA2): d.xy = a.xy * b.xy + d.xy, two IEEE fp32 FMAs in one issue slot
+__device__ __forceinline__ void ffma2(float2& d, const float2 a, const float2 b) {
+  asm("fma.rn.f32x2 %0, %1, %2, %0;"
+      : "+l"(reinterpret_cast<unsigned long long&>(d))
+      : "l"(reinterpret_cast<const unsigned long long&>(a)), "l"(reinterpret_cast<const unsigned long long&>(b)));
+}
+
+struct alignas(16) FoldedParams {
+  float2 w2d[C][3][6];  // [ci][kt][co] = (w, w) of the temporal conv with BN2 folded in; co padded to 6 (48-byte rows)
+  float2 b2d[6];        // (b, b)
+  float2 rwd[2][6];     // [x|y][co] = (w, w) of the residual 1x1 conv with BN_res folded in
+  float2 rbd[6];
   float gw[C][2], gb[C];
   float s1[C], o1[C];
-  float w2[C][C][3], b2[C];  // BN2 folded in
-  float rw[C][2], rb[C];     // BN_res folded in
   float a1, a2;
 };
 
@@ -46,7 +62,7 @@ struct SmemLayout {
   int NP;           // padded max pedestrians
   int chunk_floats; // payload floats per ring stage
   int p_bufs;       // 1 or 2
-  size_t off_bar, off_g, off_p, off_ring, total;
+  size_t off_bar, off_rtab, off_g, off_p, off_ring, total;
 };
 
 __host__ __device__ inline SmemLayout make_layout(int max_n, size_t budget, int stages) {
@@ -55,19 +71,32 @@ __host__ __device__ inline SmemLayout make_layout(int max_n, size_t budget, int 
   size_t o = (sizeof(FoldedParams) + 15) & ~size_t(15);
   L.off_bar = o;
   o += sizeof(uint64_t) * S_WARPS * S_MAX_STAGES;
+  L.off_rtab = o;
+  o += (sizeof(uint16_t) * (L.NP + 1) + 15) & ~size_t(15);
   L.off_g = o;
-  o += sizeof(float) * S_WARPS * L.NP * 8;
+  o += sizeof(float) * S_WARPS * (L.NP / 4) * G_QUAD;
   L.off_p = o;
   L.p_bufs = (L.NP <= 128) ? 2 : 1;
   o += sizeof(float) * L.p_bufs * C * T_OBS * L.NP;
   L.off_ring = o;
-  size_t per_stage = (budget - o) / (S_WARPS * stages) / sizeof(float);
+  // the ring is followed by 32 * 8 floats of slack: lanes whose column lies beyond N read (and ignore) whatever
+  // follows their row inside the allocation
+  const size_t slack = sizeof(float) * 32 * 8;
+  size_t per_stage = (budget - o - slack) / (S_WARPS * stages) / sizeof(float);
   per_stage &= ~size_t(3);
   long cf = static_cast<long>(per_stage) - S_PAD;
   if (cf > 4096) cf = 4096;  // 16 KB copies are plenty
   L.chunk_floats = static_cast<int>(cf);
-  L.total = o + sizeof(float) * S_WARPS * stages * (L.chunk_floats + S_PAD);
+  L.total = o + sizeof(float) * S_WARPS * stages * (L.chunk_floats + S_PAD) + slack;
   return L;
+}
+
+// rows of an N x N slice per ring stage: as many as fit, a multiple of four when at least four fit
+__host__ __device__ inline int rows_per_chunk(int chunk_floats, int N) {
+  int R = chunk_floats / N;
+  if (R > N) R = N;
+  if (R >= 4 && R < N) R &= ~3;
+  return R;
 }
 
 // cursor over one warp's sequence of (scene, row-chunk) copies
@@ -79,15 +108,14 @@ struct Cursor {
   const float* sl;  // base of this warp's A[t] slice
 };
 
-__device__ __forceinline__ void cursor_open(Cursor& c, int s, int S, int t, int chunk_floats,
+__device__ __forceinline__ void cursor_open(Cursor& c, int s, int S, int t, const uint16_t* __restrict__ rtab,
                                             const int32_t* __restrict__ seg_off,
                                             const int64_t* __restrict__ a_off, const float* __restrict__ A) {
   c.s = s;
   c.r0 = 0;
   if (s < S) {
     c.N = seg_off[s + 1] - seg_off[s];
-    c.R = chunk_floats / c.N;
-    if (c.R > c.N) c.R = c.N;
+    c.R = rtab[c.N];
     c.sl = A + a_off[s] + static_cast<size_t>(t) * c.N * c.N;
   } else {
     c.N = 1;
@@ -109,8 +137,9 @@ stgcn_fwd_kernel(const float* __restrict__ V, const float* __restrict__ A, const
   const int tid = threadIdx.x, lane = tid & 31, t = tid >> 5;
   const int NP = L.NP;
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + L.off_bar) + t * S_MAX_STAGES;
-  float* gbuf = reinterpret_cast<float*>(smem + L.off_g) + static_cast<size_t>(t) * NP * 8;  // [v][8]
-  float* pbuf = reinterpret_cast<float*>(smem + L.off_p);                                    // [buf][c][t][NP]
+  uint16_t* rtab = reinterpret_cast<uint16_t*>(smem + L.off_rtab);                                  // [N] -> rows per chunk
+  float* gq = reinterpret_cast<float*>(smem + L.off_g) + static_cast<size_t>(t) * (NP / 4) * G_QUAD;  // [v/4][c][4]
+  float* pbuf = reinterpret_cast<float*>(smem + L.off_p);                                           // [buf][c][t][NP]
   const int stage_floats = L.chunk_floats + S_PAD;
   float* ring = reinterpret_cast<float*>(smem + L.off_ring) + static_cast<size_t>(t) * S_STAGES * stage_floats;
 
@@ -122,12 +151,18 @@ stgcn_fwd_kernel(const float* __restrict__ V, const float* __restrict__ A, const
     fp.o1[c] = params[P_BN1_B + c] - bn[0 + c] * s1;
     const float s2 = params[P_BN2_G + c] / sqrtf(bn[15 + c] + BN_EPS);
     for (int ci = 0; ci < C; ++ci)
-      for (int k = 0; k < 3; ++k) fp.w2[c][ci][k] = params[P_TCN_W + (c * C + ci) * 3 + k] * s2;
-    fp.b2[c] = (params[P_TCN_B + c] - bn[10 + c]) * s2 + params[P_BN2_B + c];
+      for (int k = 0; k < 3; ++k) {
+        const float w = params[P_TCN_W + (c * C + ci) * 3 + k] * s2;
+        fp.w2d[ci][k][c] = make_float2(w, w);
+      }
+    const float b2 = (params[P_TCN_B + c] - bn[10 + c]) * s2 + params[P_BN2_B + c];
+    fp.b2d[c] = make_float2(b2, b2);
     const float sr = params[P_BNR_G + c] / sqrtf(bn[25 + c] + BN_EPS);
-    fp.rw[c][0] = params[P_RES_W + c * 2 + 0] * sr;
-    fp.rw[c][1] = params[P_RES_W + c * 2 + 1] * sr;
-    fp.rb[c] = (params[P_RES_B + c] - bn[20 + c]) * sr + params[P_BNR_B + c];
+    const float r0 = params[P_RES_W + c * 2 + 0] * sr, r1 = params[P_RES_W + c * 2 + 1] * sr;
+    fp.rwd[0][c] = make_float2(r0, r0);
+    fp.rwd[1][c] = make_float2(r1, r1);
+    const float rb = (params[P_RES_B + c] - bn[20 + c]) * sr + params[P_BNR_B + c];
+    fp.rbd[c] = make_float2(rb, rb);
     fp.gw[c][0] = params[P_GCN_W + c * 2 + 0];
     fp.gw[c][1] = params[P_GCN_W + c * 2 + 1];
     fp.gb[c] = params[P_GCN_B + c];
@@ -136,6 +171,7 @@ stgcn_fwd_kernel(const float* __restrict__ V, const float* __restrict__ A, const
       fp.a2 = params[P_PRELU2];
     }
   }
+  for (int n = tid + 1; n <= NP; n += S_THREADS) rtab[n] = static_cast<uint16_t>(rows_per_chunk(L.chunk_floats, n));
   if (lane == 0) {
 #pragma unroll
     for (int i = 0; i < S_STAGES; ++i) mbar_init(&full[i], 1);
@@ -148,122 +184,136 @@ stgcn_fwd_kernel(const float* __restrict__ V, const float* __restrict__ A, const
   // offsets and H's write-back lines (3.49 -> 3.43 ms per 131,072 scenes of 64)
   const uint64_t l2_pol = l2_evict_first_policy();
   Cursor pc;
-  cursor_open(pc, blockIdx.x, S, t, L.chunk_floats, seg_off, a_off, A);
+  cursor_open(pc, blockIdx.x, S, t, rtab, seg_off, a_off, A);
   auto produce = [&](int stage) {
     if (pc.s >= S) return;
     int rows = pc.N - pc.r0;
     if (rows > pc.R) rows = pc.R;
-    const float* src = pc.sl + static_cast<size_t>(pc.r0) * pc.N;
+    const float* src = pc.sl + pc.r0 * pc.N;
     const uintptr_t b = reinterpret_cast<uintptr_t>(src);
     const uintptr_t b0 = b & ~uintptr_t(15);
-    const uintptr_t e1 = (b + static_cast<uintptr_t>(rows) * pc.N * 4 + 15) & ~uintptr_t(15);
+    const uint32_t bytes = (static_cast<uint32_t>(b - b0) + static_cast<uint32_t>(rows * pc.N) * 4u + 15u) & ~15u;
     if (lane == 0) {
-      const uint32_t bytes = static_cast<uint32_t>(e1 - b0);
       mbar_arrive_expect_tx(&full[stage], bytes);
       bulk_g2s_hint(ring + stage * stage_floats, reinterpret_cast<const void*>(b0), bytes, &full[stage], l2_pol);
     }
     pc.r0 += rows;
-    if (pc.r0 >= pc.N) cursor_open(pc, pc.s + gridDim.x, S, t, L.chunk_floats, seg_off, a_off, A);
+    if (pc.r0 >= pc.N) cursor_open(pc, pc.s + gridDim.x, S, t, rtab, seg_off, a_off, A);
   };
 #pragma unroll
   for (int i = 0; i < S_STAGES; ++i) produce(i);
 
   uint32_t consumed = 0;  // chunks consumed by this warp so far (stage = consumed % STAGES)
-  // V[t] of the first scene
-  float vx[NJ], vy[NJ];
-#ifndef SSTG_STGCN_NO_PREFETCH_OFFSETS
-  // The next scene's offsets travel with its V prefetch, so the scene top does not wait for a dependent global
-  // load -> use chain (6 % of the stall samples sat on its first consumer, profiles/r1t_ncu_full_summary.csv):
-  // 3.44 -> 3.33 ms per 131,072 scenes of 64, bit-identical (profiles/r2a_ab_stgcn_po.txt).
-  // -DSSTG_STGCN_NO_PREFETCH_OFFSETS restores the in-loop loads for A/B runs.
+  // V[t] of the first scene, as (column 2 i, column 2 i + 1) pairs of the lane's columns lane + 32 j.  The next
+  // scene's offsets travel with its V prefetch, so the scene top does not wait for a dependent global load ->
+  // use chain (3.44 -> 3.33 ms per 131,072 scenes of 64, profiles/r2a_ab_stgcn_po.txt).
+  constexpr int NP2 = (NJ + 1) / 2;
+  float2 vx[NP2], vy[NP2];
   int nx_n0 = 0, nx_N = 1;
   long long nx_ao = 0;
-#endif
   auto load_v = [&](int s) {
     if (s < S) {
       const int n0 = seg_off[s], N = seg_off[s + 1] - n0;
-#ifndef SSTG_STGCN_NO_PREFETCH_OFFSETS
       nx_n0 = n0;
       nx_N = N;
       nx_ao = a_off[s];
-#endif
       const float2* vp = reinterpret_cast<const float2*>(V) + (static_cast<size_t>(n0) * T_OBS + static_cast<size_t>(t) * N);
 #pragma unroll
       for (int j = 0; j < NJ; ++j) {
         const int k = lane + 32 * j;
         const float2 v = k < N ? vp[k] : make_float2(0.f, 0.f);
-        vx[j] = v.x;
-        vy[j] = v.y;
+        if (j & 1) {
+          vx[j >> 1].y = v.x;
+          vy[j >> 1].y = v.y;
+        } else {
+          vx[j >> 1].x = v.x;
+          vy[j >> 1].x = v.y;
+        }
       }
+      if (NJ & 1) vx[NP2 - 1].y = vy[NP2 - 1].y = 0.f;
     }
   };
   load_v(blockIdx.x);
 
   int it = 0;
   for (int s = blockIdx.x; s < S; s += gridDim.x, ++it) {
-#ifndef SSTG_STGCN_NO_PREFETCH_OFFSETS
     const int n0 = nx_n0;
     const int N = nx_N;
     const float* sl = A + nx_ao + static_cast<size_t>(t) * N * N;
-#else
-    const int n0 = seg_off[s];
-    const int N = seg_off[s + 1] - n0;
-    const float* sl = A + a_off[s] + static_cast<size_t>(t) * N * N;
-#endif
-    int R = L.chunk_floats / N;
-    if (R > N) R = N;
+    const int R = rtab[N];
 
-    // ---- phase 1: g for this warp's timestep, columns owned by the lane
-    float rx[NJ], ry[NJ];
+    // ---- phase 1: g for this warp's timestep, rows (= nodes) owned by the lane, into the [quad][c][4] tile;
+    // the rows that pad N to a multiple of four get g = 0
+    float2 rx[NP2], ry[NP2];
+#pragma unroll
+    for (int i = 0; i < NP2; ++i) {
+      rx[i] = vx[i];
+      ry[i] = vy[i];
+    }
 #pragma unroll
     for (int j = 0; j < NJ; ++j) {
       const int k = lane + 32 * j;
-      rx[j] = vx[j];
-      ry[j] = vy[j];
-      if (k < N) {
-        float4 g4;
-        g4.x = fmaf(fp.gw[0][1], vy[j], fmaf(fp.gw[0][0], vx[j], fp.gb[0]));
-        g4.y = fmaf(fp.gw[1][1], vy[j], fmaf(fp.gw[1][0], vx[j], fp.gb[1]));
-        g4.z = fmaf(fp.gw[2][1], vy[j], fmaf(fp.gw[2][0], vx[j], fp.gb[2]));
-        g4.w = fmaf(fp.gw[3][1], vy[j], fmaf(fp.gw[3][0], vx[j], fp.gb[3]));
-        *reinterpret_cast<float4*>(gbuf + k * 8) = g4;
-        gbuf[k * 8 + 4] = fmaf(fp.gw[4][1], vy[j], fmaf(fp.gw[4][0], vx[j], fp.gb[4]));
+      const float x = (j & 1) ? vx[j >> 1].y : vx[j >> 1].x;
+      const float y = (j & 1) ? vy[j >> 1].y : vy[j >> 1].x;
+      if (k < ((N + 3) & ~3)) {
+        float* g = gq + (k >> 2) * G_QUAD + (k & 3);
+        const bool in = k < N;
+#pragma unroll
+        for (int c = 0; c < C; ++c) g[c * 4] = in ? fmaf(fp.gw[c][1], y, fmaf(fp.gw[c][0], x, fp.gb[c])) : 0.f;
       }
     }
     __syncwarp();
-    load_v(s + gridDim.x);  // register prefetch of the next scene's V[t]
+    load_v(s + gridDim.x);  // register prefetch of the next scene's V[t] and offsets
 
     // ---- phase 2: y[c, t, w] = sum_v g[c, t, v] A[t, v, w], streamed through the ring
-    float acc[C][NJ];
+    float2 acc[C][NJ];  // (sum over even rows, sum over odd rows) of column lane + 32 j
 #pragma unroll
     for (int c = 0; c < C; ++c)
 #pragma unroll
-      for (int j = 0; j < NJ; ++j) acc[c][j] = 0.f;
+      for (int j = 0; j < NJ; ++j) acc[c][j] = make_float2(0.f, 0.f);
 
     for (int r0 = 0; r0 < N; r0 += R) {
       const int rows = (N - r0 < R) ? (N - r0) : R;
       const int stage = consumed % S_STAGES;
       const uint32_t parity = (consumed / S_STAGES) & 1;
-      const float* src = sl + static_cast<size_t>(r0) * N;
+      const float* src = sl + r0 * N;
       const int off = static_cast<int>((reinterpret_cast<uintptr_t>(src) & 15) >> 2);
-      const float* tile = ring + stage * stage_floats + off;
+      const float* row = ring + stage * stage_floats + off + lane;   // column lane of the chunk's first row
+      const float* g = gq + (r0 >> 2) * G_QUAD;                      // r0 is a multiple of four whenever rows >= 4
       mbar_wait(&full[stage], parity);
-#pragma unroll 4
-      for (int r = 0; r < rows; ++r) {
-        const float* g = gbuf + (r0 + r) * 8;
-        const float4 g4 = *reinterpret_cast<const float4*>(g);
-        const float g5 = g[4];
-        const float* row = tile + r * N;
+      int q = 0;
+#pragma unroll 2
+      for (; q + 4 <= rows; q += 4) {
+        float4 g4[C];
+#pragma unroll
+        for (int c = 0; c < C; ++c) g4[c] = *reinterpret_cast<const float4*>(g + c * 4);
+        g += G_QUAD;
+        float2 a01[NJ], a23[NJ];
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {   // lanes beyond N read (finite or not) neighbours: their sums are never used
+          a01[j] = make_float2(row[32 * j], row[N + 32 * j]);
+          a23[j] = make_float2(row[2 * N + 32 * j], row[3 * N + 32 * j]);
+        }
+        row += 4 * N;
+#pragma unroll
+        for (int c = 0; c < C; ++c)
+#pragma unroll
+          for (int j = 0; j < NJ; ++j) ffma2(acc[c][j], a01[j], make_float2(g4[c].x, g4[c].y));
+#pragma unroll
+        for (int c = 0; c < C; ++c)
+#pragma unroll
+          for (int j = 0; j < NJ; ++j) ffma2(acc[c][j], a23[j], make_float2(g4[c].z, g4[c].w));
+      }
+      for (; q < rows; ++q) {  // N not a multiple of four: the last rows of the slice, one at a time
+        const int v = r0 + q;
+        const float* gs = gq + (v >> 2) * G_QUAD + (v & 3);
 #pragma unroll
         for (int j = 0; j < NJ; ++j) {
-          const int k = lane + 32 * j;
-          const float a = k < N ? row[k] : 0.f;
-          acc[0][j] = fmaf(g4.x, a, acc[0][j]);
-          acc[1][j] = fmaf(g4.y, a, acc[1][j]);
-          acc[2][j] = fmaf(g4.z, a, acc[2][j]);
-          acc[3][j] = fmaf(g4.w, a, acc[3][j]);
-          acc[4][j] = fmaf(g5, a, acc[4][j]);
+          const float a = row[32 * j];
+#pragma unroll
+          for (int c = 0; c < C; ++c) acc[c][j].x = fmaf(gs[c * 4], a, acc[c][j].x);
         }
+        row += N;
       }
       __syncwarp();
       produce(stage);
@@ -277,38 +327,48 @@ stgcn_fwd_kernel(const float* __restrict__ V, const float* __restrict__ A, const
 #pragma unroll
       for (int j = 0; j < NJ; ++j) {
         const int k = lane + 32 * j;
-        if (k < N) p[(c * T_OBS + t) * NP + k] = prelu(fmaf(acc[c][j], fp.s1[c], fp.o1[c]), fp.a1);
+        if (k < N) p[(c * T_OBS + t) * NP + k] = prelu(fmaf(acc[c][j].x + acc[c][j].y, fp.s1[c], fp.o1[c]), fp.a1);
       }
     __syncthreads();
 
-    // ---- phase 3: (3,1) temporal conv (+BN2) + residual branch (+BN_res) + PReLU2
-    float* Hs = H + static_cast<size_t>(n0) * (C * T_OBS);
+    // ---- phase 3: (3,1) temporal conv (+BN2) + residual branch (+BN_res) + PReLU2, two columns per FFMA2
+    float* Hs = H + static_cast<size_t>(n0) * (C * T_OBS) + t * N + lane;
+    float2 z[C][NP2];
 #pragma unroll
-    for (int j = 0; j < NJ; ++j) {
-      const int k = lane + 32 * j;
-      if (k < N) {
-        float z[C];
+    for (int co = 0; co < C; ++co)
 #pragma unroll
-        for (int co = 0; co < C; ++co) z[co] = fp.b2[co];
+      for (int i = 0; i < NP2; ++i) {
+        z[co][i] = fp.rbd[co];
+        ffma2(z[co][i], fp.rwd[0][co], rx[i]);
+        ffma2(z[co][i], fp.rwd[1][co], ry[i]);
+        z[co][i].x += fp.b2d[co].x;
+        z[co][i].y += fp.b2d[co].y;
+      }
 #pragma unroll
-        for (int kt = 0; kt < 3; ++kt) {
-          const int tt = t + kt - 1;
-          if (tt >= 0 && tt < T_OBS) {
+    for (int kt = 0; kt < 3; ++kt) {
+      const int tt = t + kt - 1;
+      if (tt >= 0 && tt < T_OBS) {
+        const float* pr = p + tt * NP + lane;
 #pragma unroll
-            for (int ci = 0; ci < C; ++ci) {
-              const float pv = p[(ci * T_OBS + tt) * NP + k];
+        for (int ci = 0; ci < C; ++ci) {
+          float2 pv[NP2];
 #pragma unroll
-              for (int co = 0; co < C; ++co) z[co] = fmaf(fp.w2[co][ci][kt], pv, z[co]);
-            }
-          }
-        }
+          for (int i = 0; i < NP2; ++i)   // the second column of an odd NJ lies beyond NP: re-read the first
+            pv[i] = make_float2(pr[ci * T_OBS * NP + 64 * i], pr[ci * T_OBS * NP + ((2 * i + 1 < NJ) ? 64 * i + 32 : 64 * i)]);
 #pragma unroll
-        for (int co = 0; co < C; ++co) {
-          const float res = fmaf(fp.rw[co][1], ry[j], fmaf(fp.rw[co][0], rx[j], fp.rb[co]));
-          Hs[(co * T_OBS + t) * N + k] = prelu(z[co] + res, fp.a2);
+          for (int co = 0; co < C; ++co)
+#pragma unroll
+            for (int i = 0; i < NP2; ++i) ffma2(z[co][i], fp.w2d[ci][kt][co], pv[i]);
         }
       }
     }
+#pragma unroll
+    for (int co = 0; co < C; ++co)
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) {
+        const float h = (j & 1) ? z[co][j >> 1].y : z[co][j >> 1].x;
+        if (lane + 32 * j < N) Hs[co * T_OBS * N + 32 * j] = prelu(h, fp.a2);
+      }
     if (L.p_bufs == 1) __syncthreads();
   }
 }
@@ -323,7 +383,7 @@ int launch_nj(const float* V, const float* A, const int32_t* seg_off, const int6
   // 227 KB for one CTA per SM; two CTAs share the SM's 228 KB (1 KB reserved per CTA)
   const int budget = CPS == 1 ? max_optin : (max_optin + 1024) / 2 - 1024;
   const SmemLayout L = make_layout(max_n, static_cast<size_t>(budget), STAGES);
-  if (L.chunk_floats < L.NP) return SSTG_ETOOBIG;
+  if (L.chunk_floats < 4 * L.NP) return SSTG_ETOOBIG;   // a ring stage holds at least four rows
   auto kern = stgcn_fwd_kernel<NJ, CPS, STAGES>;
   SSTG_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(L.total)),
                 "stgcn smem attr");
