@@ -91,12 +91,17 @@ __host__ __device__ inline SmemLayout make_layout(int max_n, size_t budget, int 
   return L;
 }
 
-// rows of an N x N slice per ring stage: as many as fit, a multiple of four when at least four fit
+// rows of an N x N slice per ring stage: the slice is cut into the fewest chunks that fit a stage, of EQUAL
+// size rounded up to a multiple of four rows (N = 64 with room for 19 rows: 4 x 16, not 20 + 20 + 20 + 4)
 __host__ __device__ inline int rows_per_chunk(int chunk_floats, int N) {
-  int R = chunk_floats / N;
-  if (R > N) R = N;
-  if (R >= 4 && R < N) R &= ~3;
-  return R;
+  const int rmax = chunk_floats / N;            // >= 4: checked at launch
+  if (rmax >= N) return N;
+  const int r4 = rmax & ~3;
+#ifdef SSTG_STGCN_UNBALANCED
+  return r4;
+#endif
+  const int n = (N + r4 - 1) / r4;              // chunks per slice
+  return (((N + n - 1) / n) + 3) & ~3;          // <= r4 because r4 is a multiple of four
 }
 
 // cursor over one warp's sequence of (scene, row-chunk) copies
@@ -211,6 +216,8 @@ stgcn_fwd_kernel(const float* __restrict__ V, const float* __restrict__ A, const
   float2 vx[NP2], vy[NP2];
   int nx_n0 = 0, nx_N = 1;
   long long nx_ao = 0;
+  // (a two-level pipeline -- offsets two scenes ahead, V one scene ahead -- measured SLOWER at the 128-register
+  //  cap of the two-CTA form: 3.00 vs 2.82 ms, profiles/r2g_ab_stgcn.txt)
   auto load_v = [&](int s) {
     if (s < S) {
       const int n0 = seg_off[s], N = seg_off[s + 1] - n0;
