@@ -71,6 +71,56 @@ __global__ void stg_write(float4* __restrict__ dst, size_t n4, float v) {
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) dst[i] = q;
 }
 
+// The graph kernel's store pattern: a CTA of `warps` warps takes 64 KB items (grid-stride); PER_WARP = true: every
+// warp streams its own contiguous 64 KB / warps slice, 512 B per instruction (what graph_build_fast_kernel does);
+// false: the whole CTA writes the item front to back, warps interleaved at 512 B.
+template <bool PER_WARP>
+__global__ void item_write(float4* __restrict__ dst, size_t n_items, float v) {
+  const int warps = blockDim.x >> 5, w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float4 q = make_float4(v, v, v, v);
+  const int item4 = 65536 / 16;            // float4 per item
+  const int slice4 = item4 / warps;
+  for (size_t it = blockIdx.x; it < n_items; it += gridDim.x) {
+    float4* base = dst + it * item4;
+    if (PER_WARP) {
+      float4* p = base + (size_t)w * slice4 + lane;
+      for (int i = 0; i < slice4; i += 32) p[i] = q;
+    } else {
+      float4* p = base + threadIdx.x;
+      for (int i = 0; i < item4; i += blockDim.x) p[i] = q;
+    }
+  }
+}
+
+// The same items written with TMA bulk stores: every warp fills its 16 KB (64 KB / warps) slice in shared memory
+// (STS.128), fences the async proxy and issues `parts` cp.async.bulk shared -> global copies.
+__global__ void item_write_bulk(float* __restrict__ dst, size_t n_items, float v, int parts) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int warps = blockDim.x >> 5, w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int slice_bytes = 65536 / warps;
+  float4* tile = reinterpret_cast<float4*>(smem + (size_t)w * slice_bytes);
+  const float4 q = make_float4(v, v, v, v);
+  const int part_bytes = slice_bytes / parts;
+  for (size_t it = blockIdx.x; it < n_items; it += gridDim.x) {
+    char* g = reinterpret_cast<char*>(dst) + it * 65536 + (size_t)w * slice_bytes;
+    for (int pI = 0; pI < parts; ++pI) {
+      // the previous bulk store that read this part must be done reading before it is overwritten
+      if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      __syncwarp();
+      float4* t4 = tile + pI * (part_bytes / 16);
+      for (int i = lane; i < part_bytes / 16; i += 32) t4[i] = q;
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) {
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(g + pI * part_bytes),
+                     "r"(smem_u32(t4)), "r"(part_bytes) : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      }
+    }
+  }
+  if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
 __global__ void copy_kernel(const float4* __restrict__ src, float4* __restrict__ dst, size_t n4) {
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) dst[i] = src[i];
@@ -112,12 +162,27 @@ int main() {
     printf("read  LDG.128 (4 in flight): %7.1f GB/s\n", bytes / ms / 1e6);
     ms = time_ms([&] { stg_write<<<sms * 8, 512>>>((float4*)dst, bytes / 16, 1.f); });
     printf("write STG.128            : %7.1f GB/s\n", bytes / ms / 1e6);
+    for (int warps : {4, 8})
+      for (int per_sm : {3, 6}) {
+        ms = time_ms([&] { item_write<true><<<sms * per_sm, warps * 32>>>((float4*)dst, bytes / 65536, 1.f); });
+        printf("write 64 KB items, per-warp slices, %d warps x %d CTAs/SM : %7.1f GB/s\n", warps, per_sm, bytes / ms / 1e6);
+        ms = time_ms([&] { item_write<false><<<sms * per_sm, warps * 32>>>((float4*)dst, bytes / 65536, 1.f); });
+        printf("write 64 KB items, CTA-contiguous,  %d warps x %d CTAs/SM : %7.1f GB/s\n", warps, per_sm, bytes / ms / 1e6);
+      }
+    cudaFuncSetAttribute(item_write_bulk, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536);
+    for (int parts : {1, 2, 4})
+      for (int per_sm : {2, 3}) {
+        ms = time_ms([&] { item_write_bulk<<<sms * per_sm, 128, 65536>>>(dst, bytes / 65536, 1.f, parts); });
+        cudaError_t e = cudaGetLastError();
+        printf("write 64 KB items, TMA bulk stores, 4 warps x %d CTAs/SM, %d parts per 16 KB slice : %7.1f GB/s %s\n", per_sm, parts,
+               bytes / ms / 1e6, e == cudaSuccess ? "" : cudaGetErrorString(e));
+      }
     ms = time_ms([&] { cudaMemsetAsync(dst, 0, bytes); });
     printf("cudaMemset               : %7.1f GB/s\n", bytes / ms / 1e6);
   }
   const int chunks[] = {2048, 4096, 4608, 8192, 16384};
   for (int cps = 1; cps <= 2; ++cps)
-    for (int warps : {4, 8, 16})
+    for (int warps : {8})
       for (int ci = 0; ci < 5; ++ci) {
         const int chunk = chunks[ci];
         auto run = [&](auto stages_tag) {
