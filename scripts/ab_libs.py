@@ -69,6 +69,8 @@ steps = [
                                         min_ade=ws["min_ade"], min_fde=ws["min_fde"]),
      lambda: torch.cat([ws["min_ade"], ws["min_fde"]])),
 ]
+Hf = torch.empty_like(ws["H"])
+steps.append(("fused_front", lambda: E.stgcn_forward_fused(dp, obs_rel, eng.params, eng.bn, H=Hf, Pws=ws["Pws"]), lambda: Hf))
 # the same kernel with INJECTED noise (the <EXACT=0, PHILOX=0> instantiation) on the first scenes of the batch
 S2 = min(S, 4096)
 P2 = S2 * N
