@@ -149,6 +149,47 @@ def test_stgcn_block_vs_oracle(golden, batch, dev):
     assert worst < TOL, worst
 
 
+@pytest.mark.parametrize("counts", [
+    [1, 2, 3, 4, 5, 6, 7, 8, 9, 30, 31, 32],            # one column per lane; row tails of 1..3 after the row quads
+    [33, 62, 63, 64, 64, 65 - 2, 34, 47, 64, 2, 61],    # two columns per lane, two CTAs per SM
+    [65, 66, 96, 127, 128, 3, 100],                     # four columns per lane, several ring chunks per slice
+    [129, 130, 200, 255, 256, 256, 131],                # eight columns per lane, 4-row chunks at N = 256
+])
+def test_stgcn_kernel_shapes_vs_oracle(golden, dev, counts):
+    """The st_gcn kernel on synthetic ragged batches that cover every template instantiation, the row-quad /
+    row-tail split of the FFMA2 aggregation (N mod 4 = 0..3), equal-sized ring chunks and lanes whose columns
+    lie beyond N -- against the oracle's st_gcn block (model.py:145-155 restated) on the SAME V and A.  A is
+    an arbitrary dense matrix here: the block does not depend on it being a Laplacian.  Tolerance 1e-5 of
+    the largest |H| of the scene (fp32: the kernel sums even and odd rows separately)."""
+    import social_stgcnn_b200 as sstg
+    from oracle import stgcnn_oracle as O
+    params, bn = golden.params("hotel")
+    P, S = O.unflatten_params(params), O.unflatten_bn(bn)
+    n = np.asarray(counts, np.int32)
+    plan = sstg.ScenePlan(n)
+    dp = plan.on(dev)
+    rng = np.random.default_rng(int(n.sum()))
+    V = (rng.standard_normal(plan.P * 16) * 0.5).astype(np.float32)
+    A = np.zeros(plan.a_floats, np.float32)
+    blocks = []
+    for i, k in enumerate(n):
+        a = (rng.standard_normal((8, k, k)) / np.sqrt(k)).astype(np.float32)
+        A[plan.a_off[i]:plan.a_off[i] + 8 * k * k] = a.ravel()
+        blocks.append(a)
+    H = sstg.stgcn_forward(dp, torch.from_numpy(V).to(dev), torch.from_numpy(A).to(dev),
+                           torch.from_numpy(params).to(dev), torch.from_numpy(bn).to(dev))
+    torch.cuda.synchronize()
+    H = H.cpu().numpy()
+    for i, k in enumerate(n):
+        o = int(plan.seg_off[i])
+        v = torch.from_numpy(V[o * 16:(o + k) * 16].reshape(8, k, 2))[None].permute(0, 3, 1, 2)
+        with torch.no_grad():
+            ref = O.stgcn_forward(P, S, v, torch.from_numpy(blocks[i])).numpy()
+        h = H[o * 40:(o + k) * 40].reshape(1, 5, 8, k)
+        assert np.isfinite(h).all()
+        assert rel_err(h, ref) < TOL, (i, int(k), rel_err(h, ref))
+
+
 def test_nll_forward(golden, batch, dev):
     """bivariate_loss per scene against the reference's eval NLL (loss_golden)."""
     import social_stgcnn_b200 as sstg
