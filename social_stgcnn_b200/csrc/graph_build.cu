@@ -281,6 +281,9 @@ graph_build_fast_kernel(const float* __restrict__ rel, const int32_t* __restrict
       float* wp = Wt + lane;
       int h = 0;
       float4 xn = *reinterpret_cast<const float4*>(xt), yn = *reinterpret_cast<const float4*>(yt);
+#ifdef SSTG_G_NO_PASS1   // profiling knob (never in the shipped build): time the store phase alone
+      h = cN;
+#endif
       for (; h + 4 <= cN; h += 4) {
         const float4 xh = xn, yh = yn;  // loaded one group ahead (the read past row N stays inside the padded row)
         xn = *reinterpret_cast<const float4*>(xt + ((h + 4 < NP) ? h + 4 : h));
@@ -346,6 +349,9 @@ graph_build_fast_kernel(const float* __restrict__ rel, const int32_t* __restrict
               o.y = fmaf(-(w4[u].y * dh[u]), dk.y, 0.f);
               o.z = fmaf(-(w4[u].z * dh[u]), dk.z, 0.f);
               o.w = fmaf(-(w4[u].w * dh[u]), dk.w, 0.f);
+#ifdef SSTG_G_NO_STORE   // profiling knob (never in the shipped build): time the arithmetic alone
+              if (o.x == 123.456f)
+#endif
               *reinterpret_cast<float4*>(adst + u * stride) = o;  // plain stores: st.global.cs (evict-first) measured 3 % slower
             }
             wsrc += 4 * stride;
