@@ -312,3 +312,26 @@ def test_validate_epoch_and_sharded_evaluator(golden, dev):
     a2, f2, n = ev.evaluate(d.plan_obs.n_peds, d.obs_traj_rel, d.pred_traj_rel, d.obs_traj[:, :, -1].contiguous(),
                             K=20, seed=5)
     assert n == 181 and abs(a1 - a2) < 1e-12 and abs(f1 - f2) < 1e-12
+
+
+@pytest.mark.parametrize("split", ["test", "val"])
+def test_nuscenes_dummy_dataset_graphs_are_the_reference(dev, split):
+    """BASELINE config 5 (nuScenes_mini graph construction): TrajectoryDataset(delim=' ') on the reference's own
+    nuScenes stand-in data == the unmodified reference (real networkx normalized Laplacian), scene by scene:
+    V_obs, V_tr bit-exact and A_obs (T = 8), A_tr (T = 12, built lazily) BIT-IDENTICAL
+    (tests/golden/nuscenes_golden.npz, made by tests/golden/make_nuscenes_golden.py)."""
+    import os
+    from tests.common import GOLD
+    from social_stgcnn_b200.utils import TrajectoryDataset
+    g = np.load(os.path.join(GOLD, "nuscenes_golden.npz"))
+    d = TrajectoryDataset(os.path.join(GOLD, "datasets", "nuscenes_mini_dummy", split) + "/", obs_len=8, pred_len=12,
+                          skip=1, norm_lap_matr=True, delim=" ", device=dev)
+    n = g[f"{split}.n_peds"]
+    assert len(d) == len(n) and [e - s for s, e in d.seq_start_end] == n.tolist()
+    for name, lst in (("V_obs", d.v_obs), ("A_obs", d.A_obs), ("V_tr", d.v_pred), ("A_tr", d.A_pred)):
+        got = np.concatenate([np.asarray(t.numpy(), np.float32).ravel() for t in lst])
+        ref = g[f"{split}.{name}"]
+        assert got.shape == ref.shape, name
+        assert np.array_equal(got.view(np.int32), ref.view(np.int32)), (name, float(np.abs(got - ref).max()))
+    item = d[len(d) - 1]
+    assert len(item) == 10 and tuple(item[7].shape) == (8, int(n[-1]), int(n[-1])) and tuple(item[9].shape) == (12, int(n[-1]), int(n[-1]))

@@ -219,30 +219,50 @@ def test_exchange_argument_is_not_overridden_by_the_environment(monkeypatch):
         Pl.DistributedTrainer(Eng(), exchange="mpi")
 
 
+def _windowing_digest(path, delim):
+    import hashlib
+    from social_stgcnn_b200.utils import load_scenes
+    seqs, rels, masks, nl, counts, max_peds = load_scenes(path, 8, 12, 1, 0.002, 1, delim)
+    seq_all, rel_all = np.concatenate(seqs), np.concatenate(rels)
+    cum = [0] + np.cumsum(counts).tolist()
+    h = hashlib.sha256()
+    for a in (seq_all[:, :, :8], seq_all[:, :, 8:], rel_all[:, :, :8], rel_all[:, :, 8:], np.concatenate(nl)):
+        h.update(np.ascontiguousarray(a, np.float32).tobytes())
+    h.update(np.ascontiguousarray(np.asarray(list(zip(cum, cum[1:])), np.int64)).tobytes())
+    return {"scenes": len(seqs), "peds": int(seq_all.shape[0]), "max_peds_in_frame": int(max_peds),
+            "sha256": h.hexdigest()}
+
+
 def test_windowing_digests_of_every_shipped_split():
     """utils.load_scenes on all 15 ETH/UCY splits == the digests the REAL reference TrajectoryDataset produced
     (tests/golden/make_windowing_golden.py: scene / pedestrian counts, max_peds_in_frame and the SHA-256 of
     obs_traj | pred_traj | obs_traj_rel | pred_traj_rel | non_linear_ped | seq_start_end).  The dataset files
     live in the reference tree and do not travel: skipped where /root/reference is absent (eth/test, the one
     committed file, is covered element-wise above)."""
-    import hashlib
     import json
-    from social_stgcnn_b200.utils import load_scenes
     root = "/root/reference/datasets"
     if not os.path.isdir(root):
         pytest.skip("reference dataset files not present on this box")
     gold = json.load(open(os.path.join(GOLD, "windowing_golden.json")))
-    assert len(gold) == 15
-    for key, ref in sorted(gold.items()):
+    eth_ucy = {k: v for k, v in gold.items() if not k.startswith("nuscenes_mini_dummy/")}
+    assert len(eth_ucy) == 15
+    for key, ref in sorted(eth_ucy.items()):
         if key.endswith("/train") and not os.environ.get("SSTG_TEST_ALL_SPLITS"):
             continue                                    # the five train splits add ~20 s; opt-in
-        seqs, rels, masks, nl, counts, max_peds = load_scenes(f"{root}/{key}/", 8, 12, 1, 0.002, 1, "\t")
-        seq_all, rel_all = np.concatenate(seqs), np.concatenate(rels)
-        cum = [0] + np.cumsum(counts).tolist()
-        h = hashlib.sha256()
-        for a in (seq_all[:, :, :8], seq_all[:, :, 8:], rel_all[:, :, :8], rel_all[:, :, 8:], np.concatenate(nl)):
-            h.update(np.ascontiguousarray(a, np.float32).tobytes())
-        h.update(np.ascontiguousarray(np.asarray(list(zip(cum, cum[1:])), np.int64)).tobytes())
-        got = {"scenes": len(seqs), "peds": int(seq_all.shape[0]), "max_peds_in_frame": int(max_peds),
-               "sha256": h.hexdigest()}
-        assert got == ref, key
+        assert _windowing_digest(f"{root}/{key}/", "\t") == ref, key
+
+
+def test_windowing_of_the_nuscenes_dummy_splits():
+    """BASELINE config 5: the reference's own nuScenes stand-in (complete_nuscenes_setup.create_dummy_data,
+    committed as a data fixture by tests/golden/make_nuscenes_golden.py; space-delimited, rows ordered by
+    pedestrian, not by frame) windowed by utils.load_scenes == the reference's TrajectoryDataset(delim=' '):
+    80 / 143 / 333 scenes, identical tensors (SHA-256)."""
+    import json
+    gold = json.load(open(os.path.join(GOLD, "windowing_golden.json")))
+    for split, scenes in (("test", 80), ("val", 143), ("train", 333)):
+        ref = gold[f"nuscenes_mini_dummy/{split}"]
+        assert ref["scenes"] == scenes
+        assert _windowing_digest(os.path.join(GOLD, "datasets", "nuscenes_mini_dummy", split) + "/", " ") == ref, split
+    from social_stgcnn_b200.utils import load_scenes
+    with pytest.raises(ValueError):                     # the default tab delimiter fails like the reference's read_file
+        load_scenes(os.path.join(GOLD, "datasets", "nuscenes_mini_dummy", "test") + "/", 8, 12, 1, 0.002, 1, "\t")
