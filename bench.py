@@ -186,6 +186,35 @@ def cpu_port_throughput(n_scenes, procs, seed=0):
     return done / dt, done, dt
 
 
+def cpu_port_phases(n_scenes=32, seed=0):
+    """Single-process time of the oracle port's three phases on `n_scenes` scenes of the workload (SURVEY 8d asks for
+    graph build and forward / evaluation separately): seconds per scene of seq_to_graph, of the eval forward and of the
+    20-sample ADE/FDE."""
+    import torch
+    torch.set_num_threads(1)
+    from oracle import stgcnn_oracle as O
+    params, bn = load_weights()
+    P_, S_ = O.unflatten_params(params), O.unflatten_bn(bn)
+    obs_rel, pred_rel, last = [t.numpy() for t in synth_batch(n_scenes, N_PEDS, 8765 + seed)]
+    g = torch.Generator().manual_seed(seed)
+    tg = tf = ts = 0.0
+    for i in range(n_scenes):
+        sl = slice(i * N_PEDS, (i + 1) * N_PEDS)
+        eps = torch.randn(K_SAMPLES, 12, N_PEDS, 2, generator=g).numpy()
+        t0 = time.perf_counter()
+        V_obs, A_obs = O.seq_to_graph(obs_rel[sl])
+        t1 = time.perf_counter()
+        with torch.no_grad():
+            out = O.model_forward(P_, S_, V_obs, A_obs)
+        V_pred = O.vpred_tn5(out).numpy()
+        t2 = time.perf_counter()
+        O.sample_ade_fde(V_pred, np.ascontiguousarray(pred_rel[sl].transpose(2, 0, 1)), last[sl], eps)
+        t3 = time.perf_counter()
+        tg, tf, ts = tg + (t1 - t0), tf + (t2 - t1), ts + (t3 - t2)
+    return {"graph_build_ms_per_scene": 1e3 * tg / n_scenes, "forward_ms_per_scene": 1e3 * tf / n_scenes,
+            "sample_ade_fde_ms_per_scene": 1e3 * ts / n_scenes, "scenes": n_scenes, "threads": 1}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -729,7 +758,8 @@ def run_ours(args):
                 ref_t = " | " + open(p).read().strip()
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                                     "sample": f"{done} scenes of {N} peds in {dt:.1f}s, oracle port, one process per "
-                                              f"core (single process: {v1:.1f} scenes/s){ref_t}"}
+                                              f"core (single process: {v1:.1f} scenes/s){ref_t}",
+                                    "phases_single_thread": cpu_port_phases()}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
