@@ -26,10 +26,17 @@ namespace sstg {
 
 namespace {
 
+#ifndef SSTG_E_KU
+#define SSTG_E_KU 5
+#endif
+constexpr int E_KU = SSTG_E_KU;  // samples a thread advances together: 5 (K = 20 -> 4 sample classes, 128 threads) or 4 (5 classes,
+                                 // 160 threads: no unpaired fifth sample, every trajectory operation packed); A/B knob -DSSTG_E_KU=4|5
+static_assert(E_KU == 4 || E_KU == 5, "E_KU");
 constexpr int E_PEDS = 32;  // pedestrians per CTA: small CTAs (128 threads, 64 registers in the throughput form) so that
                             // 8 fit an SM and one CTA's latency-bound prologue overlaps the sampling loops of the others
-constexpr int E_SUB = 4;
+constexpr int E_SUB = 20 / E_KU;
 constexpr int E_THREADS = E_PEDS * E_SUB;
+constexpr int E_CTAS = E_KU == 5 ? 8 : 6;   // CTAs per SM of the throughput form at 64 registers
 
 struct Philox {
   static constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
@@ -136,7 +143,6 @@ __device__ __forceinline__ int find_scene(const int32_t* __restrict__ seg_off, i
   return lo;
 }
 
-constexpr int E_KU = 5;  // samples a thread advances together (K = 20 -> one pass of 4 x 5)
 // Of the two sample pairs (0,1), (2,3) of a thread, how many advance as PACKED FP32 pairs in the throughput form (the rest,
 // and sample 4, as scalar chains; same roundings either way).  ncu shows the heavy half of the FMA pipe as the busiest unit
 // (74 %: Philox's IMAD.WIDE plus the packed FP32), but un-packing does not relieve it: measured 2.13 / 2.18 / 2.24 ms per
@@ -151,7 +157,7 @@ constexpr int E_TRAJ_PACKED = SSTG_E_TRAJ_PACKED;
 // PHILOX : draw the noise in-kernel instead of reading eps.
 // EXTRA  : eps_out / pred_abs requested (raw_data_dict, test.py:105).
 template <bool EXACT, bool PHILOX, bool EXTRA>
-__global__ void __launch_bounds__(E_THREADS, (EXACT || EXTRA) ? 4 : 8)
+__global__ void __launch_bounds__(E_THREADS, (EXACT || EXTRA) ? 4 : E_CTAS)
 sample_ade_fde_kernel(const float* __restrict__ Vpred, const float* __restrict__ Vtr,
                       const float* __restrict__ last_obs, const int32_t* __restrict__ seg_off, int S, int K,
                       const float* __restrict__ eps, uint64_t seed, float* __restrict__ eps_out,
@@ -218,15 +224,16 @@ sample_ade_fde_kernel(const float* __restrict__ Vpred, const float* __restrict__
   // ground-truth displacements and start position -- are issued before any of the arithmetic, so that a CTA
   // pays ONE memory latency here, not two.
   {
-    constexpr int PER = T_PRED * E_PEDS / E_THREADS;  // 3
+    constexpr int PER = (T_PRED * E_PEDS + E_THREADS - 1) / E_THREADS;  // 3
     float in[PER][5];
     bool ok[PER];
 #pragma unroll
     for (int u = 0; u < PER; ++u) {
       const int i = tid + u * E_THREADS;
-      const int t = i / E_PEDS, pl = i - t * E_PEDS;
+      const bool inr = i < T_PRED * E_PEDS;
+      const int t = inr ? i / E_PEDS : 0, pl = inr ? i - t * E_PEDS : 0;
       const int N = sc_N[pl];
-      ok[u] = N > 0;
+      ok[u] = inr && N > 0;
       const int n0 = sc_n0[pl], nl = p_base + pl - n0;
       const float* vp = Vpred + static_cast<size_t>(n0) * 60 + t * N + nl;  // (c, t, n) at (c*12 + t)*N + n
 #pragma unroll
@@ -309,7 +316,7 @@ sample_ade_fde_kernel(const float* __restrict__ Vpred, const float* __restrict__
       }
       // throughput path (fp32 distances, nothing extra to store): samples (0,1) and (2,3) of the thread advance
       // as packed pairs, sample 4 alone -- bit-identical to the scalar loop, ~10 % fewer instructions
-      constexpr bool PACK = !EXACT && !EXTRA && E_KU == 5;
+      constexpr bool PACK = !EXACT && !EXTRA;
       float2 cxp[2], cyp[2], accp[2], fdp[2];
 #pragma unroll
       for (int q = 0; q < 2; ++q) cxp[q] = cyp[q] = accp[q] = fdp[q] = make_float2(0.f, 0.f);
@@ -329,7 +336,7 @@ sample_ade_fde_kernel(const float* __restrict__ Vpred, const float* __restrict__
             box_muller_pair<false>(ra, rb, exq[0][q], eyq[0][q]);
             box_muller_pair<true>(ra, rb, exq[1][q], eyq[1][q]);
           }
-          box_muller2(draw(4), e2[0][4], e2[1][4]);
+          if constexpr (E_KU == 5) box_muller2(draw(4), e2[0][4], e2[1][4]);
         } else {
 #pragma unroll
           for (int i = 0; i < E_KU; ++i) {
