@@ -40,6 +40,10 @@ constexpr int S_THREADS = S_WARPS * 32;
 constexpr int S_MAX_STAGES = 4;
 constexpr int S_PAD = 8;       // floats of slack per stage for the aligned-superset copies
 constexpr int G_QUAD = 4 * C;  // floats per row quad of the g tile: [channel][4 rows]
+#ifndef SSTG_STGCN_UNROLL
+#define SSTG_STGCN_UNROLL 2
+#endif
+constexpr int S_UNROLL = SSTG_STGCN_UNROLL;  // row quads per trip of the aggregation loop (A/B knob: 1 / 2 / 4)
 
 // packed FP32 (sm_100 FFMA2): d.xy = a.xy * b.xy + d.xy, two IEEE fp32 FMAs in one issue slot
 __device__ __forceinline__ void ffma2(float2& d, const float2 a, const float2 b) {
@@ -289,7 +293,7 @@ stgcn_fwd_kernel(const float* __restrict__ V, const float* __restrict__ A, const
       const float* g = gq + (r0 >> 2) * G_QUAD;                      // r0 is a multiple of four whenever rows >= 4
       mbar_wait(&full[stage], parity);
       int q = 0;
-#pragma unroll 2
+#pragma unroll S_UNROLL
       for (; q + 4 <= rows; q += 4) {
         float4 g4[C];
 #pragma unroll
