@@ -139,6 +139,55 @@ def test_dense_crowds_properties(golden, dev):
         assert np.abs(rx["min_fde"][sl].cpu().numpy() - of).max() < 2e-6 * max(1.0, of.max()), s
 
 
+def test_full_shard_of_config3_is_consistent_with_small_batches(golden, dev):
+    """BASELINE config 3 at the bench's full per-GPU size (131,072 scenes x 64 pedestrians: 8.4 M pedestrians, a 17 GB
+    adjacency buffer of 2^32 floats): the adjacency, H and V_pred of scenes at the start, in the middle
+    (around the 2^31-float mark of A, where a 32-bit signed element index would wrap) and at the end of the batch are BIT-IDENTICAL to what the same scenes give as a
+    batch of their own -- scenes are independent, so any offset overflow or cross-scene leak would show -- and
+    the per-pedestrian minima are finite, ordered (ADE <= FDE is not required, but both > 0) and monotone in K."""
+    import social_stgcnn_b200 as sstg
+    from social_stgcnn_b200 import engine as E
+    free, _ = torch.cuda.mem_get_info(dev)
+    if free < 40e9:
+        pytest.skip("needs ~40 GB of free device memory")
+    S, N = 131072, 64
+    g = torch.Generator().manual_seed(77)
+    P = S * N
+    vel = torch.rand(P, 2, 1, generator=g) - 0.5
+    obs = vel + 0.1 * torch.randn(P, 2, 8, generator=g)
+    obs[:, :, 0] = 0
+    pred = vel + 0.1 * torch.randn(P, 2, 12, generator=g)
+    last = torch.rand(P, 2, generator=g) * 20 - 10
+    obs, pred, last = obs.to(dev), pred.to(dev), last.to(dev)
+    params, bn = golden.params("zara1")
+    eng = sstg.InferenceEngine(params, bn, dev)
+    plan = sstg.ScenePlan(np.full(S, N, np.int32))
+    assert plan.a_floats == S * 8 * N * N == 2 ** 32
+    r = eng.infer(plan, obs, pred, last, K=20, seed=3, want_vtr=False)
+    torch.cuda.synchronize()
+    for k in ("H", "V_pred", "min_ade", "min_fde"):
+        assert torch.isfinite(r[k]).all(), k
+    assert float(r["min_ade"].min()) > 0.0 and float(r["min_fde"].min()) > 0.0
+    ade20 = r["min_ade"].clone()
+    mid = (2 ** 31) // (8 * N * N) - 128          # the scenes whose adjacency blocks straddle float offset 2^31
+    eng2 = sstg.InferenceEngine(params, bn, dev)
+    for lo in (0, mid, S - 256):
+        sub = sstg.ScenePlan(np.full(256, N, np.int32))
+        sl = slice(lo * N, (lo + 256) * N)
+        dps = sub.on(dev)
+        V, A = E.graph_build(dps, obs[sl].contiguous(), 8)
+        H = E.stgcn_forward(dps, V, A, eng2.params, eng2.bn)
+        vp = E.txpcnn_forward(dps, H, eng2.params)
+        torch.cuda.synchronize()
+        a_big = r["A_obs"][lo * 8 * N * N:(lo + 256) * 8 * N * N]
+        assert torch.equal(a_big.view(torch.int32), A.view(torch.int32)), lo
+        assert torch.equal(r["H"][lo * N * 40:(lo + 256) * N * 40].view(torch.int32), H.view(torch.int32)), lo
+        assert torch.equal(r["V_pred"][lo * N * 60:(lo + 256) * N * 60].view(torch.int32), vp.view(torch.int32)), lo
+    r10 = eng.infer(plan, obs, pred, last, K=10, seed=3, want_vtr=False)
+    torch.cuda.synchronize()
+    assert bool((ade20 <= r10["min_ade"]).all())
+
+
 def test_large_scenes_256_pedestrians(golden, dev):
     """BASELINE config 4: 256 pedestrians per scene (the N x N aggregation stress; one A[t] slice is
     256 KB > shared memory, so st_gcn streams it in row chunks; TXP-CNN tiles are single scenes).
