@@ -193,6 +193,10 @@ graph_build_kernel(const float* __restrict__ rel, const int32_t* __restrict__ se
 // ---------------------------------------------------------------------------------------
 constexpr int F_WARPS = 4;
 constexpr int F_THREADS = F_WARPS * 32;
+#ifndef SSTG_G_U1
+#define SSTG_G_U1 1
+#endif
+constexpr int G_U1 = SSTG_G_U1;  // row groups (of 4) of pass 1 per trip (A/B knob)
 
 // Requires T % 4 == 0 (8 and 12 in every configuration) and N <= 64.
 template <int NJ>
@@ -284,6 +288,7 @@ graph_build_fast_kernel(const float* __restrict__ rel, const int32_t* __restrict
 #ifdef SSTG_G_NO_PASS1   // profiling knob (never in the shipped build): time the store phase alone
       h = cN;
 #endif
+#pragma unroll G_U1
       for (; h + 4 <= cN; h += 4) {
         const float4 xh = xn, yh = yn;  // loaded one group ahead (the read past row N stays inside the padded row)
         xn = *reinterpret_cast<const float4*>(xt + ((h + 4 < NP) ? h + 4 : h));
