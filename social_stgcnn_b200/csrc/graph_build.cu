@@ -16,6 +16,8 @@
 //          to fp32 -- the reference's rounding points.
 //   fp32 : rsqrt on the same fp32 squared distance, 4-way split fp32 row sums; within
 //          ~3e-7 relative of the fp64 result (tests bound it at 2e-6; bar is 1e-5).
+#include <cstdlib>
+
 #include "sstg_common.cuh"
 
 namespace sstg {
@@ -393,13 +395,235 @@ graph_build_fast_kernel(const float* __restrict__ rel, const int32_t* __restrict
   }
 }
 
+// The same work with WARP-level items (scene, timestep): no CTA barrier anywhere.  In the kernel above the four
+// warps of a CTA stage their inputs together, so they also run pass 1 (arithmetic only) and pass 2 (the store
+// burst) together, and an SM holds just three such groups: built without stores the kernel takes 2.81 ms, without
+// pass 1 3.02 ms, with both 3.55 ms -- the phases overlap only partly.  Here every warp fetches its own
+// timestep's displacements (4-byte loads at a 2 T float stride: the 8 timesteps of a pedestrian share one
+// 32-byte sector, so DRAM traffic is unchanged and the repeats hit L2), prefetches the next item into registers
+// and walks its items independently: 12 actors per SM instead of 3.  Arithmetic and results are identical.
+template <int NJ>
+__global__ void __launch_bounds__(F_THREADS)
+graph_build_warp_kernel(const float* __restrict__ rel, const int32_t* __restrict__ seg_off,
+                        const int64_t* __restrict__ a_off, int S, int T, int NP, int wtile,
+                        float* __restrict__ V, float* __restrict__ A) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  float* xs = reinterpret_cast<float*>(smem_raw) + warp * NP;                      // [warp][NP]
+  float* ys = reinterpret_cast<float*>(smem_raw) + (F_WARPS + warp) * NP;          // [warp][NP]
+  float* dst = reinterpret_cast<float*>(smem_raw) + (2 * F_WARPS + warp) * NP;     // [warp][NP] ds
+  float* Wt = reinterpret_cast<float*>(smem_raw) + 3 * F_WARPS * NP + static_cast<size_t>(warp) * wtile;  // [warp][N*N]
+  pdl_wait();
+  pdl_release();
+  const long long items = static_cast<long long>(S) * T;
+  const long long W = static_cast<long long>(gridDim.x) * F_WARPS;
+  long long it = static_cast<long long>(blockIdx.x) * F_WARPS + warp;
+  // Software pipeline per warp, in registers.  Under the store stream a global load takes 6-7 us -- longer than
+  // one item (~6 us) -- so the displacements run TWO items ahead and the offsets they need two more.
+  struct Meta {
+    int t, n0, N;
+    long long ao;
+  };
+  auto load_offsets = [&](long long item, Meta& o) {
+    if (item < items) {
+      const int sc = static_cast<int>(item / T);
+      o.t = static_cast<int>(item - static_cast<long long>(sc) * T);
+      o.n0 = seg_off[sc];
+      o.N = seg_off[sc + 1] - o.n0;
+      o.ao = a_off[sc];
+    }
+  };
+  auto load_rel = [&](long long item, const Meta& m, float (&x)[NJ], float (&y)[NJ]) {  // offsets of `item` are in `m`
+    if (item < items) {
+      const float* r = rel + static_cast<size_t>(m.n0) * 2 * T + m.t;
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) {
+        const int k = lane + 32 * j;
+        if (k < m.N) {
+          x[j] = r[static_cast<size_t>(k) * 2 * T];
+          y[j] = r[static_cast<size_t>(k) * 2 * T + T];
+        }
+      }
+    }
+  };
+  Meta m0 = {0, 0, 0, 0}, m1 = m0, m2 = m0, o3 = m0, o4 = m0;   // items it, it+W, it+2W (data), it+3W, it+4W (offsets)
+  float px0[NJ], py0[NJ], px1[NJ], py1[NJ], px2[NJ], py2[NJ];
+#pragma unroll
+  for (int j = 0; j < NJ; ++j) px0[j] = py0[j] = px1[j] = py1[j] = px2[j] = py2[j] = 0.f;
+  load_offsets(it, m0);
+  load_offsets(it + W, m1);
+  load_offsets(it + 2 * W, m2);
+  load_offsets(it + 3 * W, o3);
+  load_offsets(it + 4 * W, o4);
+  load_rel(it, m0, px0, py0);
+  load_rel(it + W, m1, px1, py1);
+  load_rel(it + 2 * W, m2, px2, py2);
+  int ct = 0, cn0 = 0, cN = 0;
+  long long cao = 0;
+  while (it < items) {
+    ct = m0.t;
+    cn0 = m0.n0;
+    cN = m0.N;
+    cao = m0.ao;
+    // stage this warp's x / y rows and write the node tensor V[t] (utils.py:42)
+    float2* Vs = reinterpret_cast<float2*>(V + static_cast<size_t>(cn0) * T * 2) + static_cast<size_t>(ct) * cN;
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+      const int k = lane + 32 * j;
+      if (k < cN) {
+        xs[k] = px0[j];
+        ys[k] = py0[j];
+        Vs[k] = make_float2(px0[j], py0[j]);
+      }
+    }
+    __syncwarp();
+    // rotate; request the displacements of item it + 3W (offsets two trips old) and the offsets of it + 5W
+    m0 = m1;
+    m1 = m2;
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+      px0[j] = px1[j], py0[j] = py1[j];
+      px1[j] = px2[j], py1[j] = py2[j];
+    }
+    m2 = o3;
+    load_rel(it + 3 * W, m2, px2, py2);
+    o3 = o4;
+    load_offsets(it + 5 * W, o4);
+    it += W;
+    const float* xt = xs;
+    const float* yt = ys;
+    const int ct0 = ct - warp;   // the shared body below addresses its slice as ct0 + warp
+    {
+      float xk[NJ], yk[NJ], acc[NJ][2];
+      bool kv[NJ];
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) {
+        const int k = lane + 32 * j;
+        kv[j] = k < cN;
+        xk[j] = kv[j] ? xt[k] : 0.f;
+        yk[j] = kv[j] ? yt[k] : 0.f;
+        acc[j][0] = acc[j][1] = 0.f;
+      }
+      // ---- pass 1: weights once, column sums on the fly (4 rows per iteration)
+      float* wp = Wt + lane;
+      int h = 0;
+      float4 xn = *reinterpret_cast<const float4*>(xt), yn = *reinterpret_cast<const float4*>(yt);
+#ifdef SSTG_G_NO_PASS1   // profiling knob (never in the shipped build): time the store phase alone
+      h = cN;
+#endif
+#pragma unroll G_U1
+      for (; h + 4 <= cN; h += 4) {
+        const float4 xh = xn, yh = yn;  // loaded one group ahead (the read past row N stays inside the padded row)
+        xn = *reinterpret_cast<const float4*>(xt + ((h + 4 < NP) ? h + 4 : h));
+        yn = *reinterpret_cast<const float4*>(yt + ((h + 4 < NP) ? h + 4 : h));
+        const float xa[4] = {xh.x, xh.y, xh.z, xh.w}, ya[4] = {yh.x, yh.y, yh.z, yh.w};
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+#pragma unroll
+          for (int j = 0; j < NJ; ++j) {
+            const float dx = xa[u] - xk[j], dy = ya[u] - yk[j];
+            const float w = inv_dist(fmaf(dx, dx, dy * dy));
+            acc[j][u & 1] += w;
+            if (kv[j]) wp[32 * j] = w;
+          }
+          wp += cN;
+        }
+      }
+      for (; h < cN; ++h) {
+        const float xh = xt[h], yh = yt[h];
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+          const float dx = xh - xk[j], dy = yh - yk[j];
+          const float w = inv_dist(fmaf(dx, dx, dy * dy));
+          acc[j][0] += w;
+          if (kv[j]) wp[32 * j] = w;
+        }
+        wp += cN;
+      }
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) {
+        const int k = lane + 32 * j;
+        const float lkk = acc[j][0] + acc[j][1];  // the diagonal contributed w(0) = 0: d = 1 + off-diagonal sum
+        if (kv[j]) {
+          dst[k] = rsqrt_fast(1.f + lkk);
+          Wt[k * cN + k] = -lkk;  // so that -(W_kk) ds_k ds_k = (d_k - 1) / d_k
+        }
+      }
+      __syncwarp();
+      // ---- pass 2: A_hk = -(w_hk ds_h) ds_k, streamed out
+      float* At = A + cao + static_cast<size_t>(ct0 + warp) * cN * cN;
+      if ((cN & 3) == 0) {
+        const int lpr = cN >> 2;           // 16-byte chunks per row (<= 16 for N <= 64)
+        const int rpp = 32 / lpr;          // rows per warp pass
+        const int rr = lane / lpr, c4 = (lane - rr * lpr) * 4;
+        const float4 dk = *reinterpret_cast<const float4*>(dst + c4);
+        if (rr < rpp) {
+          const float* wsrc = Wt + rr * cN + c4;
+          float* adst = At + static_cast<size_t>(rr) * cN + c4;
+          const int stride = rpp * cN;
+          int hh = rr;
+          for (; hh + 3 * rpp < cN; hh += 4 * rpp) {
+            float4 w4[4];
+            float dh[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              w4[u] = *reinterpret_cast<const float4*>(wsrc + u * stride);
+              dh[u] = dst[hh + u * rpp];
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              float4 o;
+              o.x = fmaf(-(w4[u].x * dh[u]), dk.x, 0.f);
+              o.y = fmaf(-(w4[u].y * dh[u]), dk.y, 0.f);
+              o.z = fmaf(-(w4[u].z * dh[u]), dk.z, 0.f);
+              o.w = fmaf(-(w4[u].w * dh[u]), dk.w, 0.f);
+#ifdef SSTG_G_NO_STORE   // profiling knob (never in the shipped build): time the arithmetic alone
+              if (o.x == 123.456f)
+#endif
+              *reinterpret_cast<float4*>(adst + u * stride) = o;  // plain stores: st.global.cs (evict-first) measured 3 % slower
+            }
+            wsrc += 4 * stride;
+            adst += 4 * stride;
+          }
+          for (; hh < cN; hh += rpp) {
+            const float4 w4 = *reinterpret_cast<const float4*>(wsrc);
+            const float dh = dst[hh];
+            float4 o;
+            o.x = fmaf(-(w4.x * dh), dk.x, 0.f);
+            o.y = fmaf(-(w4.y * dh), dk.y, 0.f);
+            o.z = fmaf(-(w4.z * dh), dk.z, 0.f);
+            o.w = fmaf(-(w4.w * dh), dk.w, 0.f);
+            *reinterpret_cast<float4*>(adst) = o;
+            wsrc += stride;
+            adst += stride;
+          }
+        }
+      } else {
+        float dk[NJ];
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) dk[j] = kv[j] ? dst[lane + 32 * j] : 0.f;
+        for (int hh = 0; hh < cN; ++hh) {
+          const float dh = dst[hh];
+#pragma unroll
+          for (int j = 0; j < NJ; ++j) {
+            const int k = lane + 32 * j;
+            if (kv[j]) At[static_cast<size_t>(hh) * cN + k] = fmaf(-(Wt[hh * cN + k] * dh), dk[j], 0.f);
+          }
+        }
+      }
+    }
+    __syncwarp();   // the next item overwrites this warp's rows and tile
+  }
+}
+
 template <int NJ>
 int launch_fast(const float* rel, const int32_t* seg_off, const int64_t* a_off, int S, int T, int max_n, float* V,
                 float* A, cudaStream_t st) {
   const int NP = (max_n + 3) & ~3;
   const int wtile = (max_n * max_n + 3) & ~3;
   const size_t smem = sizeof(float) * (static_cast<size_t>(3 * F_WARPS * NP) + static_cast<size_t>(F_WARPS) * wtile);
-  auto kern = graph_build_fast_kernel<NJ>;
+  const char* coop = getenv("SSTG_GRAPH_COOP");   // A/B knob: 1 = the CTA-cooperative kernel (4 timesteps per item)
+  auto kern = (coop && coop[0] == '1') ? graph_build_fast_kernel<NJ> : graph_build_warp_kernel<NJ>;
   if (smem > 48 * 1024)
     SSTG_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)),
                   "graph_build_fast smem attr");
