@@ -18,6 +18,11 @@ void note_cuda_error(cudaError_t e, const char* where) {
 
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
+int sstg_xtile_pairs() {
+  const char* e = std::getenv("SSTG_XTILE_PAIRS");
+  return (e && e[0] == '3' && e[1] == '2') ? 32 : SSTG_XTILE_MAX_PAIRS;
+}
+
 bool pdl_enabled() {
   const char* e = std::getenv("SSTG_NO_PDL");
   return !(e && e[0] == '1');
@@ -56,7 +61,9 @@ int sstg_plan_host(const int32_t* n_peds_host, int32_t S, int32_t T, int32_t* se
   int64_t total = 0;
   for (int32_t s = 0; s < S; ++s) total += n_peds_host[s] > 0 ? n_peds_host[s] : 0;
   int64_t cap64 = (total + 295) / 296;
-  const int32_t cap = static_cast<int32_t>(cap64 < 8 ? 8 : (cap64 > SSTG_XTILE_COLS ? SSTG_XTILE_COLS : cap64));
+  int32_t cap = static_cast<int32_t>(cap64 < 8 ? 8 : (cap64 > SSTG_XTILE_COLS ? SSTG_XTILE_COLS : cap64));
+  const int32_t max_pairs = ::sstg::sstg_xtile_pairs();
+  if (cap > 2 * max_pairs) cap = 2 * max_pairs;
   int64_t ped = 0, af = 0;
   int32_t mx = 0, nt = 0, cols = 0, scenes = 0, pairs = 0;
   int32_t wcol = 1, wmax = 0;  // shared-memory columns of the current tile in the odd-start layout of txpcnn_wino.cu
@@ -70,7 +77,7 @@ int sstg_plan_host(const int32_t* n_peds_host, int32_t S, int32_t T, int32_t* se
     if (n > mx) mx = n;
     // close the current TXP-CNN tile if this scene does not fit any more
     if (scenes > 0 && (cols + n > cap || scenes == SSTG_XTILE_MAX_SCENES ||
-                       pairs + ((n + 1) >> 1) > SSTG_XTILE_MAX_PAIRS)) {
+                       pairs + ((n + 1) >> 1) > max_pairs)) {
       tile_off_host[++nt] = s;
       cols = 0;
       scenes = 0;

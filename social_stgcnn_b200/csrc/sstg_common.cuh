@@ -129,6 +129,7 @@ __device__ __forceinline__ float inv_dist(float sq) { return sq >= 1.17549435e-3
 
 #endif  // __CUDACC__
 
+int sstg_xtile_pairs();  // sstg_api.cu: column pairs per TXP-CNN tile, 64 or (SSTG_XTILE_PAIRS=32) 32 -- read by the planner AND the launcher
 bool pdl_enabled();  // sstg_api.cu: false when the environment has SSTG_NO_PDL=1 (read at every launch)
 
 #ifdef __CUDACC__

@@ -44,7 +44,9 @@ using namespace txp;
 #ifndef WINO_NPF_CONST
 #define WINO_NPF_CONST 9   // the same for constant-bank filters: they wait in UNIFORM registers (36 of the warp's 63),
 #endif                     // so a deeper ring costs no vector register.  Both must divide 3 * COT (ring phase).
-constexpr int W_PAIRS = SSTG_XTILE_MAX_PAIRS;  // 64 column pairs per tile
+// W_PAIRS (template parameter): column pairs per tile = threads per channel group.  64 (two 64-pedestrian scenes, 128-thread
+// CTAs, two per SM) or 32 (64-thread CTAs, four per SM: the same warps per SM, but four independent tiles whose per-layer
+// barriers and scalar epilogues drift apart -- sstg_plan_host cuts such tiles when SSTG_XTILE_PAIRS=32).
 constexpr int W_U0 = 8 * 3 * 12 * 4;           // layer 0: [ci 8][kh 3][co 12][4]
 constexpr int W_UL = 12 * 3 * 12 * 4;          // layers 1..4
 constexpr int W_UTOTAL = W_U0 + 4 * W_UL;      // 8064 floats
@@ -106,8 +108,8 @@ __global__ void wino_filter_kernel(const float* __restrict__ params, float* __re
 // global-memory round trip behind three barriers: 12.5 % of the stall samples of the plain kernel
 // (profiles/r1am_ncu_full_summary.csv) although only 2 % of its instructions -- leaves the critical path.  Layer 0 then reads
 // the staging tile, everything else is unchanged (same arithmetic, same order: bit-identical results).
-template <int NSPLIT, bool CONSTW, bool PF>
-__global__ void __launch_bounds__(NSPLIT * W_PAIRS, 2)
+template <int NSPLIT, bool CONSTW, bool PF, int W_PAIRS = SSTG_XTILE_MAX_PAIRS>
+__global__ void __launch_bounds__(NSPLIT * W_PAIRS, 128 / W_PAIRS)
 txpcnn_wino_kernel(const float* __restrict__ Hin, const int32_t* __restrict__ seg_off,
                    const int32_t* __restrict__ tile_off, int n_tiles, const float* __restrict__ params,
                    float* __restrict__ out, int W_WP) {
@@ -399,11 +401,12 @@ txpcnn_wino_kernel(const float* __restrict__ Hin, const int32_t* __restrict__ se
   }
 }
 
-template <int NSPLIT, bool CONSTW, bool PF = false>
+template <int NSPLIT, bool CONSTW, bool PF = false, int W_PAIRS = SSTG_XTILE_MAX_PAIRS>
 int launch_wino_v(const float* H, const int32_t* seg_off, const int32_t* tile_off, int n_tiles, const float* params,
                   float* out, int W_WP, int grid_cap, cudaStream_t st) {
   const size_t smem = ((sizeof(WSmemT<CONSTW, PF>) + 15) & ~size_t(15)) + sizeof(float) * (X_ROWS + (PF ? 40 : 0)) * W_WP;
-  auto kern = txpcnn_wino_kernel<NSPLIT, CONSTW, PF>;
+  auto kern = txpcnn_wino_kernel<NSPLIT, CONSTW, PF, W_PAIRS>;
+  grid_cap = grid_cap * (SSTG_XTILE_MAX_PAIRS / W_PAIRS);
   SSTG_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)),
                 "txpcnn_wino smem attr");
   const int grid = n_tiles < grid_cap ? n_tiles : grid_cap;
@@ -443,6 +446,8 @@ int launch_wino(const float* H, const int32_t* seg_off, const int32_t* tile_off,
   // (then n_tiles * 60 floats of `out` also exceed the 8,064-float staging area by far)
   if (n_tiles >= grid_cap && wino_const_allowed()) {
     if constexpr (NSPLIT == 2) {
+      if (sstg_xtile_pairs() == 32)   // tiles of <= 32 pairs (sstg_plan_host under the same knob): 64-thread CTAs, four per SM
+        return launch_wino_v<NSPLIT, true, false, 32>(H, seg_off, tile_off, n_tiles, params, out, W_WP, grid_cap, st);
       if (wino_prefetch())
         return launch_wino_v<NSPLIT, true, true>(H, seg_off, tile_off, n_tiles, params, out, W_WP, grid_cap, st);
     }
