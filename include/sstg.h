@@ -120,8 +120,8 @@ int sstg_stgcn_forward_fused(const float* rel, const int32_t* seg_off, int32_t S
  *        social_stgcnn.forward (model.py:198)
  *   tile_off [n_tiles+1] from sstg_plan_host (device copy); tile_cols from sstg_plan_host
  *   (0 = unknown: the kernel then reserves shared memory for the widest possible tile).
- * Scenes of up to 128 pedestrians run the Winograd F(2,3) kernel (txpcnn_wino.cu), larger
- * ones and the training forward the direct FFMA2 kernel (txpcnn_fwd.cu).
+ * Inference runs the Winograd F(2,3) kernel (txpcnn_wino.cu: 64-pair tiles, or 128-pair tiles when the batch
+ * holds scenes of more than 128 pedestrians), the training forward the direct FFMA2 kernel (txpcnn_fwd.cu).
  * NOTE (the library's only global state): when the batch fills the GPU (n_tiles >= 2 x SMs) the Winograd
  * kernel reads its transformed filters from a per-device __constant__ bank that this call refreshes in
  * stream order (the head of `out` serves as staging before the kernel overwrites it).  Calls with DIFFERENT

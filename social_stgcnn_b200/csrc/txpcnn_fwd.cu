@@ -364,10 +364,13 @@ int launch_txpcnn_forward(const float* H, const int32_t* seg_off, const int32_t*
                           float* bn) {
   if (n_tiles == 0) return SSTG_OK;
   const bool save = Usave != nullptr && Xsave != nullptr;
-  // inference on scenes of up to 128 pedestrians: the Winograd F(2,3) kernel (txpcnn_wino.cu)
-  if (!save && max_n <= X_COLS) {
+  // inference: the Winograd F(2,3) kernel (txpcnn_wino.cu) -- 64-pair tiles for scenes of up to 128 pedestrians,
+  // 128-pair tiles (256-thread CTAs) when the batch holds larger scenes (a scene > 128 columns is a tile of its own)
+  if (!save && max_n <= SSTG_MAX_PEDS) {
     const int mode = txpcnn_wino_mode();
-    if (mode != 0) return launch_txpcnn_forward_wino(H, seg_off, tile_off, n_tiles, params, out, mode, tile_cols, st);
+    if (mode != 0)
+      return launch_txpcnn_forward_wino(H, seg_off, tile_off, n_tiles, params, out, mode,
+                                        max_n <= X_COLS ? tile_cols : -(max_n + 4), st);
   }
   // widest tile: up to X_COLS columns of up to MAX_SCENES scenes, or one big scene;
   // one zero separator column before every scene and one after the last

@@ -51,6 +51,7 @@ constexpr int W_U0 = 8 * 3 * 12 * 4;           // layer 0: [ci 8][kh 3][co 12][4
 constexpr int W_UL = 12 * 3 * 12 * 4;          // layers 1..4
 constexpr int W_UTOTAL = W_U0 + 4 * W_UL;      // 8064 floats
 constexpr int W_WP_MAX = 200;                  // widest tile row: 128 columns + up to 2 separators per scene
+constexpr int W_WP_BIG = 264;                  // ... of the 128-pair form: one scene of up to 256 columns
 
 __constant__ float c_U[W_UTOTAL + 4 * 32];  // transformed filters of the launch in flight (CONSTW variant);
                                             // the tail pads the prefetch ring's run past the last filter
@@ -406,7 +407,7 @@ int launch_wino_v(const float* H, const int32_t* seg_off, const int32_t* tile_of
                   float* out, int W_WP, int grid_cap, cudaStream_t st) {
   const size_t smem = ((sizeof(WSmemT<CONSTW, PF>) + 15) & ~size_t(15)) + sizeof(float) * (X_ROWS + (PF ? 40 : 0)) * W_WP;
   auto kern = txpcnn_wino_kernel<NSPLIT, CONSTW, PF, W_PAIRS>;
-  grid_cap = grid_cap * (SSTG_XTILE_MAX_PAIRS / W_PAIRS);
+  grid_cap = (grid_cap / 2) * (128 / W_PAIRS);   // CTAs per SM: 1 / 2 / 4 for 128 / 64 / 32 pairs per tile
   SSTG_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)),
                 "txpcnn_wino smem attr");
   const int grid = n_tiles < grid_cap ? n_tiles : grid_cap;
@@ -437,13 +438,20 @@ bool wino_prefetch() {
 
 template <int NSPLIT>
 int launch_wino(const float* H, const int32_t* seg_off, const int32_t* tile_off, int n_tiles, const float* params,
-                float* out, int W_WP, cudaStream_t st) {
+                float* out, int W_WP, cudaStream_t st, bool big = false) {
   int dev = 0, sms = 148;
   SSTG_CUDA_TRY(cudaGetDevice(&dev), "cudaGetDevice");
   SSTG_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev), "sm count");
   const int grid_cap = 2 * sms;  // 255 registers x 128 threads: two CTAs per SM
   // the constant-bank variant pays a ~6 us refresh per launch: worth it once the persistent grid is full
   // (then n_tiles * 60 floats of `out` also exceed the 8,064-float staging area by far)
+  if constexpr (NSPLIT == 2) {
+    if (big) {   // scenes of 129..256 pedestrians: 128 pairs per tile, 256 threads, one CTA per SM
+      if (n_tiles >= sms && wino_const_allowed())
+        return launch_wino_v<NSPLIT, true, false, 128>(H, seg_off, tile_off, n_tiles, params, out, W_WP, grid_cap, st);
+      return launch_wino_v<NSPLIT, false, false, 128>(H, seg_off, tile_off, n_tiles, params, out, W_WP, grid_cap, st);
+    }
+  }
   if (n_tiles >= grid_cap && wino_const_allowed()) {
     if constexpr (NSPLIT == 2) {
       if (sstg_xtile_pairs() == 32)   // tiles of <= 32 pairs (sstg_plan_host under the same knob): 64-thread CTAs, four per SM
@@ -466,10 +474,17 @@ int txpcnn_wino_mode() {
 }
 
 // tile_cols_hint: an upper bound of the shared-memory columns any tile of this batch needs
-// (1 + sum over its scenes of N_s + gap), or <= 0 for the worst case.
+// (1 + sum over its scenes of N_s + gap), 0 for the worst case of the 64-pair form, or NEGATIVE:
+// -(pedestrians of the largest scene + 4) for batches with scenes of 129..256 pedestrians (128-pair form).
 int launch_txpcnn_forward_wino(const float* H, const int32_t* seg_off, const int32_t* tile_off, int n_tiles,
                                const float* params, float* out, int mode, int tile_cols_hint, cudaStream_t st) {
   if (n_tiles == 0) return SSTG_OK;
+  if (tile_cols_hint < 0) {   // -(columns of the largest scene + 4): the batch holds scenes of more than 128 pedestrians
+    int wpb = (-tile_cols_hint + 3) & ~3;
+    if (wpb > W_WP_BIG) wpb = W_WP_BIG;
+    if (wpb < W_WP_MAX) wpb = W_WP_MAX;     // smaller scenes still share tiles of up to 128 columns + separators
+    return launch_wino<2>(H, seg_off, tile_off, n_tiles, params, out, wpb, st, true);
+  }
   int wp = (tile_cols_hint > 0 && tile_cols_hint < W_WP_MAX) ? tile_cols_hint : W_WP_MAX;
   wp = (wp + 3) & ~3;
   if (wp > W_WP_MAX) wp = W_WP_MAX;

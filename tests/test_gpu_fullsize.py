@@ -327,6 +327,38 @@ def test_winograd_constant_bank_filters_equal_shared_memory_filters(golden, dev)
         assert torch.equal(got, outs[ck][1]), ck
 
 
+def test_winograd_for_scenes_of_up_to_256_pedestrians_equals_the_direct_kernel(golden, dev):
+    """Batches with scenes of 129..256 pedestrians run the Winograd TXP-CNN in its 128-pair form (256-thread CTAs; a scene
+    of more than 128 columns is a tile of its own, smaller scenes still share tiles): the constant-bank and the
+    shared-memory filter variants must be bit-identical, and both within 1e-5 of the direct FFMA2 kernel
+    (SSTG_TXP_WINO=0) that served these sizes before -- on a batch large enough for the full grid and on a small one."""
+    import social_stgcnn_b200 as sstg
+    rng = np.random.default_rng(21)
+    for counts in (np.concatenate([np.full(150, 256), rng.integers(129, 257, 120), rng.integers(2, 129, 300)]),
+                   np.array([256, 3, 200, 129, 64, 255, 130, 7])):
+        n = rng.permutation(counts).astype(np.int32)
+        plan = sstg.ScenePlan(n)
+        dp = plan.on(dev)
+        H = torch.from_numpy(rng.standard_normal(plan.P * 40).astype(np.float32)).to(dev)
+        prm = torch.from_numpy(golden.params("univ")[0]).to(dev)
+        a = sstg.txpcnn_forward(dp, H, prm).clone()
+        os.environ["SSTG_TXP_FILTERS"] = "smem"
+        try:
+            b = sstg.txpcnn_forward(dp, H, prm).clone()
+        finally:
+            os.environ.pop("SSTG_TXP_FILTERS", None)
+        os.environ["SSTG_TXP_WINO"] = "0"
+        try:
+            c = sstg.txpcnn_forward(dp, H, prm).clone()
+        finally:
+            os.environ.pop("SSTG_TXP_WINO", None)
+        torch.cuda.synchronize()
+        assert torch.isfinite(a).all()
+        assert torch.equal(a, b)
+        scale = float(c.abs().max())
+        assert float((a - c).abs().max()) <= 1e-5 * scale, float((a - c).abs().max()) / scale
+
+
 @pytest.mark.skipif(os.environ.get("SSTG_TEST_EXPERIMENTAL") != "1",
                     reason="SSTG_TXP_PREFETCH is an unmeasured A/B variant: run with SSTG_TEST_EXPERIMENTAL=1 (under a timeout)")
 def test_winograd_next_tile_prefetch_variant_is_bit_identical(golden, dev):
