@@ -266,3 +266,50 @@ def test_windowing_of_the_nuscenes_dummy_splits():
     from social_stgcnn_b200.utils import load_scenes
     with pytest.raises(ValueError):                     # the default tab delimiter fails like the reference's read_file
         load_scenes(os.path.join(GOLD, "datasets", "nuscenes_mini_dummy", "test") + "/", 8, 12, 1, 0.002, 1, "\t")
+
+
+def test_plan_host_properties_on_random_batches():
+    """sstg_plan_host on random ragged batches (hypothesis): prefix sums, 16-byte aligned adjacency blocks that are
+    large enough, and a TXP-CNN tile table that covers every scene exactly once while respecting the tile limits
+    (columns <= cap unless a single scene is larger, <= 32 scenes, <= 64 column pairs)."""
+    from hypothesis import given, settings, strategies as st
+    import social_stgcnn_b200 as sstg
+
+    @settings(max_examples=60, deadline=None)
+    @given(st.lists(st.integers(1, 256), min_size=1, max_size=400), st.sampled_from([8, 12]))
+    def check(n, T):
+        p = sstg.ScenePlan(n, T=T)
+        n = np.asarray(n)
+        assert p.S == n.size and p.P == int(n.sum()) and p.max_n == int(n.max())
+        assert np.array_equal(p.seg_off, np.concatenate([[0], np.cumsum(n)]))
+        assert np.all(p.a_off % 4 == 0) and np.all(np.diff(p.a_off) >= T * n * n) and p.a_floats == p.a_off[-1]
+        t = p.tile_off
+        assert t[0] == 0 and t[-1] == p.S and np.all(np.diff(t) >= 1) and len(t) == p.n_tiles + 1
+        cap = min(128, max(8, -(-p.P // 296)))
+        for a, b in zip(t[:-1], t[1:]):
+            cols, pairs = int(n[a:b].sum()), int(((n[a:b] + 1) // 2).sum())
+            assert b - a <= 32
+            assert (cols <= cap and pairs <= 64) or b - a == 1
+        assert p.tile_cols >= int(n.max()) + 2
+
+    check()
+
+
+def test_shard_bounds_properties_on_random_batches():
+    """parallel.shard_bounds (hypothesis): a contiguous, ordered, complete partition for any world size, and no shard
+    heavier than the ideal share plus the heaviest scene."""
+    from hypothesis import given, settings, strategies as st
+    from social_stgcnn_b200 import parallel as Pl
+
+    @settings(max_examples=80, deadline=None)
+    @given(st.lists(st.integers(1, 64), min_size=0, max_size=300), st.integers(1, 8))
+    def check(n, world):
+        b = Pl.shard_bounds(n, world)
+        assert len(b) == world and b[0][0] == 0 and b[-1][1] == len(n)
+        assert all(lo <= hi for lo, hi in b) and all(b[i][1] == b[i + 1][0] for i in range(world - 1))
+        if n:
+            c = Pl.scene_cost(n)
+            for lo, hi in b:
+                assert c[lo:hi].sum() <= c.sum() / world + c.max() + 1e-6
+
+    check()
