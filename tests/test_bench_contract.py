@@ -40,3 +40,43 @@ def test_our_arm_refuses_to_run_without_cuda():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1", "--warmup", "0"],
                        capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert r.returncode != 0 and "no CPU fallback" in (r.stderr + r.stdout)
+
+
+import pytest  # noqa: E402
+
+
+@pytest.mark.gpu
+def test_our_arm_prints_one_contract_line_on_the_gpu():
+    """bench.py (our arm) on a small shard: ONE JSON line on stdout with every key of the driver's contract and of the
+    tier contract (roofline, e2e with the bytes it copies, gpu_launches, clocks), a config equal to bench_config()."""
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    S = 4096
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "2", "--warmup", "3",
+                        "--scenes-per-gpu", str(S), "--no-train", "--no-cpu-baseline"],
+                       capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    sys.path.insert(0, ROOT)
+    import bench
+    assert d["metric"] == bench.METRIC and d["unit"] == "scenes/s" and d["n_gpus"] == 1 and d["steps"] == 2 and d["warmup"] == 3
+    assert d["higher_is_better"] is True and d["scaling"] == "weak" and d["vs_baseline"] is None
+    assert d["dtype"] == "f32" and d["data"] == "synthetic" and d["config"] == bench.bench_config(S, 1)
+    assert d["value"] > 0 and abs(d["ms_per_step"] * 1e-3 * d["value"] - S) < 1e-6 * S
+    rf = d["roofline"]
+    assert rf["bound"] == "hbm" and rf["unit"] == "GB/s" and rf["kernel"] == "stgcn_fwd_kernel"
+    assert abs(rf["frac"] - rf["achieved"] / rf["peak"]) < 1e-12 and rf["achieved"] > 0
+    assert rf["algorithmic_bytes_per_launch"] == (64 * 64 + 32 * 64 * 64 + 160 * 64) * S
+    e = d["e2e"]
+    assert e["unit"] == "scenes/s" and e["value"] > 0
+    assert e["h2d_bytes_per_step"] == S * 64 * 168 and e["d2h_bytes_per_step"] == S * 64 * 16
+    assert d["gpu_launches"] in (4 * 2, 5 * 2)           # + the Winograd filter refresh when the grid is full
+    assert set(d["kernels"]) == {"graph_build", "stgcn_forward", "txpcnn_forward", "sample_ade_fde"}
+    assert abs(sum(k["share"] for k in d["kernels"].values()) - 1.0) < 1e-3
+    c = d["clocks"]
+    assert "sm_mhz" in c and "reasons" in c and not ({"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"} & set(c["reasons"]))
+    assert d["e2e_compact"]["identical_to_fp32_interface"] is True
+    assert 0.1 < d["result"]["ade"] < 5.0 and d["result"]["peds"] == S * 64
