@@ -34,7 +34,7 @@ using namespace sstg;
 
 extern "C" {
 
-int sstg_version(void) { return 100; }
+int sstg_version(void) { return 110; }  // 110: + sstg_peer_exchange_apply_local, sticky exchange status
 
 const char* sstg_error_string(int code) {
   switch (code) {
