@@ -341,8 +341,16 @@ def run_eth_leg(dev):
         ade_, fde_, _ = driver.evaluate(d, eng, KSTEPS=K_SAMPLES, seed=i)
     torch.cuda.synchronize()
     t2 = time.perf_counter()
+    driver.evaluate(d, eng, KSTEPS=K_SAMPLES, seed=0, graph=True)          # captures the split's pipeline once
+    torch.cuda.synchronize()
+    t3 = time.perf_counter()
+    for i in range(reps):
+        driver.evaluate(d, eng, KSTEPS=K_SAMPLES, seed=0, graph=True)      # replays (each ends with the D2H of the sums)
+    torch.cuda.synchronize()
+    t4 = time.perf_counter()
     return {"scenes": len(d), "pedestrians": int(d.obs_traj.shape[0]), "dataset_build_ms": (t1 - t0) * 1e3,
             "evaluate_ms": (t2 - t1) / reps * 1e3, "scenes_per_s_evaluate": len(d) * reps / (t2 - t1),
+            "evaluate_ms_cuda_graph": (t4 - t3) / reps * 1e3,
             "ade": ade_, "fde": fde_,
             "what": "utils.TrajectoryDataset + driver.evaluate (= test.py:18-127) on datasets/eth/test, eth checkpoint; "
                     "the unmodified reference needs ~10 minutes for its five test splits on 8 CPU cores (SURVEY 8c)"}

@@ -33,19 +33,33 @@ def _rel_to_abs(dp, rel_blocks, init, T):
 
 
 def evaluate(dataset, engine: E.InferenceEngine, KSTEPS: int = 20, seed: int = 0, eps: Optional[torch.Tensor] = None,
-             want_raw: bool = False, exact: bool = True):
+             want_raw: bool = False, exact: bool = True, graph: bool = False):
     """test() of the reference (test.py:18-127) over a whole split.
 
     Returns (ade_, fde_, raw_data_dict): the means over ALL pedestrians of the per-pedestrian
     minima over KSTEPS samples (test.py:121-126), and -- if `want_raw` -- the reference's
     raw_data_dict {step: {'obs', 'trgt', 'pred': [KSTEPS arrays]}} of absolute trajectories
     (test.py:87-105), step counted from 1.  `exact` keeps the reference's fp64 rounding islands
-    (graph, distances); `eps` injects the standard-normal noise (layout (K,12,N,2) per scene)."""
+    (graph, distances); `eps` injects the standard-normal noise (layout (K,12,N,2) per scene).
+    `graph=True` (in-kernel noise, no raw output): the split's pipeline is captured once into a CUDA graph
+    (InferenceEngine.capture, cached on the dataset per engine / KSTEPS / seed / mode) and replayed -- a test split
+    of a few hundred scenes is launch-bound, and the replay is one driver call instead of five kernel launches."""
     dev = engine.device
     pk = _packed(dataset, dev)
     plan = dataset.plan_obs
-    r = engine.infer(plan, pk["obs_rel"], pk["pred_rel"], pk["last_obs"], KSTEPS, eps=eps, seed=seed,
-                     graph_fp64=exact, fp64_dist=exact, want_pred=want_raw)
+    if graph and eps is None and not want_raw:
+        cache = dataset.__dict__.setdefault("_graphs", {})
+        key = (id(engine), int(KSTEPS), int(seed), bool(exact))
+        g = cache.get(key)
+        if g is None:
+            g = cache[key] = engine.capture(plan, KSTEPS, seed=seed, graph_fp64=exact, fp64_dist=exact)
+            g.replay(pk["obs_rel"], pk["pred_rel"], pk["last_obs"])     # the split's tensors into the static buffers, once
+        else:
+            g.replay()
+        r = g.out
+    else:
+        r = engine.infer(plan, pk["obs_rel"], pk["pred_rel"], pk["last_obs"], KSTEPS, eps=eps, seed=seed,
+                         graph_fp64=exact, fp64_dist=exact, want_pred=want_raw)
     P = plan.P
     ade_ = float(r["min_ade"].sum()) / P
     fde_ = float(r["min_fde"].sum()) / P

@@ -397,6 +397,15 @@ class InferenceEngine:
         out["eps"], out["pred_abs"] = r["eps"], r["pred_abs"]
         return out
 
+    def capture(self, plan: ScenePlan, K: int = 20, *, seed: int = 0, graph_fp64: bool = False,
+                fp64_dist: bool = False, fused: bool = False, want_vtr: bool = True) -> "GraphedInference":
+        """The whole pipeline of `infer` for a FIXED plan captured once into a CUDA graph: small batches (a test split
+        of a few hundred scenes) are launch-bound -- five to six kernels of a few microseconds each -- and a graph
+        replay issues them with one driver call.  Returns a GraphedInference whose static input tensors are filled by
+        the caller and whose `replay()` returns the same dict as `infer`."""
+        return GraphedInference(self, plan, K, seed=seed, graph_fp64=graph_fp64, fp64_dist=fp64_dist, fused=fused,
+                                want_vtr=want_vtr)
+
     def infer_host(self, plan: ScenePlan, obs_rel, pred_rel, last_obs, K: int = 20, *, chunk_scenes: int = 8192,
                    seed: int = 0, compact=None, fused: bool = True, taper: bool = True, **kw):
         """End-to-end call with HOST buffers (numpy or CPU tensors, ideally pinned): the batch is
@@ -480,6 +489,44 @@ class InferenceEngine:
     @staticmethod
     def d2h_bytes(plan: ScenePlan) -> int:
         return plan.P * 2 * 8
+
+
+class GraphedInference:
+    """`InferenceEngine.infer` for one fixed ScenePlan as a CUDA graph (torch.cuda.CUDAGraph: the capture records the
+    kernel launches libsstg.so issues on the capturing stream).  Inputs live in static device tensors
+    (`obs_rel`, `pred_rel`, `last_obs`): copy new data into them, call `replay()`, read the results -- views of static
+    buffers, valid until the next replay.  The engine's weights are read at replay time, so `load_weights` is seen.
+    The Philox seed is baked into the graph (kernel arguments are captured by value)."""
+
+    def __init__(self, engine: "InferenceEngine", plan: ScenePlan, K: int, **kw):
+        dev = engine.device
+        self.engine, self.plan, self.K = engine, plan, int(K)
+        f = torch.float32
+        self.obs_rel = torch.zeros(plan.P, 2, L.T_OBS, dtype=f, device=dev)
+        self.pred_rel = torch.zeros(plan.P, 2, L.T_PRED, dtype=f, device=dev)
+        self.last_obs = torch.zeros(plan.P, 2, dtype=f, device=dev)
+        # a private engine view: its own workspace, the parent's weight tensors (shared storage)
+        self._eng = InferenceEngine.__new__(InferenceEngine)
+        self._eng.device, self._eng.params, self._eng.bn = dev, engine.params, engine.bn
+        self._eng._ws, self._eng._cap, self._eng._pin = {}, {}, {}
+        plan.on(dev)                                   # offset tables uploaded before the capture
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):                  # warm-up outside the capture: module loading, workspace allocation
+            self._eng.infer(plan, self.obs_rel, self.pred_rel, self.last_obs, self.K, **kw)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.out = self._eng.infer(plan, self.obs_rel, self.pred_rel, self.last_obs, self.K, **kw)
+
+    def replay(self, obs_rel=None, pred_rel=None, last_obs=None):
+        """Optionally copy new inputs (device or host tensors) into the static buffers, then launch the graph."""
+        for dst, src in ((self.obs_rel, obs_rel), (self.pred_rel, pred_rel), (self.last_obs, last_obs)):
+            if src is not None:
+                dst.copy_(torch.as_tensor(src), non_blocking=True)
+        self.graph.replay()
+        return self.out
 
 
 # --------------------------------------------------------------------------

@@ -335,3 +335,38 @@ def test_nuscenes_dummy_dataset_graphs_are_the_reference(dev, split):
         assert np.array_equal(got.view(np.int32), ref.view(np.int32)), (name, float(np.abs(got - ref).max()))
     item = d[len(d) - 1]
     assert len(item) == 10 and tuple(item[7].shape) == (8, int(n[-1]), int(n[-1])) and tuple(item[9].shape) == (12, int(n[-1]), int(n[-1]))
+
+
+def test_graph_captured_evaluation_equals_the_plain_pipeline(golden, dev):
+    """InferenceEngine.capture / driver.evaluate(graph=True): the split's whole pipeline replayed from ONE CUDA graph
+    gives bit-identical per-pedestrian minima and the same dataset ADE/FDE as the kernel-by-kernel calls, sees new
+    weights (load_weights) and new inputs (replay(...)) without a re-capture."""
+    import social_stgcnn_b200 as sstg
+    from social_stgcnn_b200 import driver
+    from social_stgcnn_b200.utils import TrajectoryDataset
+    d = TrajectoryDataset(os.path.join(GOLD, "datasets", "eth", "test") + "/", obs_len=8, pred_len=12, skip=1,
+                          norm_lap_matr=True, device=dev)
+    params, bn = golden.params("eth")
+    eng = sstg.InferenceEngine(params, bn, dev)
+    a0, f0, _ = driver.evaluate(d, eng, KSTEPS=20, seed=4)
+    ref_ade = eng.infer(d.plan_obs, d.packed["obs_rel"], d.packed["pred_rel"], d.packed["last_obs"], 20, seed=4,
+                        graph_fp64=True, fp64_dist=True)["min_ade"].clone()
+    for _ in range(3):                                   # first call captures, the others replay
+        a1, f1, _ = driver.evaluate(d, eng, KSTEPS=20, seed=4, graph=True)
+        assert (a1, f1) == (a0, f0)
+    g = next(iter(d._graphs.values()))
+    torch.cuda.synchronize()
+    assert torch.equal(g.out["min_ade"], ref_ade)
+    # new weights are seen by the captured graph (it reads the engine's parameter tensors at replay time)
+    p2, b2 = golden.params("zara1")
+    eng.load_weights(p2, b2)
+    a2, f2, _ = driver.evaluate(d, eng, KSTEPS=20, seed=4, graph=True)
+    a3, f3, _ = driver.evaluate(d, eng, KSTEPS=20, seed=4)
+    assert (a2, f2) == (a3, f3) and (a2, f2) != (a0, f0)
+    # new inputs through replay(): the same scenes with the displacement order of the pedestrians' coordinates swapped
+    sw = d.packed["obs_rel"].flip(1).contiguous()
+    r = g.replay(obs_rel=sw)
+    torch.cuda.synchronize()
+    want = eng.infer(d.plan_obs, sw, d.packed["pred_rel"], d.packed["last_obs"], 20, seed=4, graph_fp64=True,
+                     fp64_dist=True)["min_ade"]
+    assert torch.equal(r["min_ade"], want)
